@@ -1,0 +1,154 @@
+/*
+ * libsigops -- C ABI of the B200-native batch signature engine.
+ *
+ * This header is the drop-in boundary that replaces the reference's gpu.rs / shader.rs layer
+ * (wgpu device + WGSL templating + multi-shader pipelines).  The reference has no FFI today: its
+ * boundary is a set of Rust `pub async fn`s; a Rust maintainer binds these C entry points inside
+ * the bodies of those functions (see INTEGRATION.md and rust/src/ffi.rs).  Each entry point cites
+ * the reference interface it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - all pointers are HOST pointers unless the name ends in `_device`; buffers are caller-owned;
+ *   - every function is blocking (except `_device`, which is stream-ordered) and thread-safe
+ *     (calls are serialised internally);
+ *   - return value 0 = success; nonzero = CUDA / runtime failure, which the Rust shim maps to
+ *     `Err(ShaderFailureError)` (src/lib.rs:12-14).  There is NO CPU fallback: without a usable
+ *     CUDA device every compute entry point fails with a nonzero code and sigops_last_error()
+ *     says why;
+ *   - byte layouts are exactly the reference's:
+ *       k1/r1 signature  64 B  r_be[32] || s_be[32] with the y parity of R in bit 7 of byte 32
+ *                               (src/wgsl/signature.wgsl:6-21, src/tests/mod.rs:151-163)
+ *       message          32 B  big-endian prehash (fuel_crypto::Message)
+ *       recovered key    64 B  X_be[32] || Y_be[32]  (src/wgsl/main/secp256k1_ecdsa_main_4.wgsl:44-51)
+ *       ed25519 sig      64 B  R_compressed[32] || s_le[32]   (src/ed25519_eddsa.rs:37)
+ *       ed25519 key      32 B  compressed A                   (src/ed25519_eddsa.rs:38)
+ */
+#ifndef SIGOPS_H
+#define SIGOPS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIGOPS_CURVE_SECP256K1 0
+#define SIGOPS_CURVE_SECP256R1 1
+#define SIGOPS_CURVE_ED25519 2
+
+/* status byte values written by the ecrecover entry points */
+#define SIGOPS_STATUS_OK 0
+#define SIGOPS_STATUS_INVALID 1 /* r==0, s==0, r>=n, s>=n, x=r not on curve, or Q = infinity */
+
+/* Device pool.  Replaces `get_device_and_queue` (src/gpu.rs:5-35), which creates and destroys a wgpu
+ * device on every API call; here the context (streams, device buffers, constant tables) persists.
+ * device_ids == NULL or n_devices <= 0: use every visible CUDA device (or SIGOPS_GPUS=<count> of them).
+ * Calling a compute entry point without sigops_init() initialises lazily with the defaults. */
+int sigops_init(const int* device_ids, int n_devices);
+int sigops_shutdown(void);
+int sigops_num_devices(void);
+/* Last error message of the calling process ("" if none). */
+const char* sigops_last_error(void);
+
+/* secp256k1_ecdsa::ecrecover / ecrecover_single_shader  (src/secp256k1_ecdsa.rs:61-66,215-219).
+ * sigs: n*64 B, msgs: n*32 B, out_pubkeys: n*64 B, out_status: n bytes or NULL.
+ * out_pubkeys[i] is 64 zero bytes when out_status[i] != 0.  n == 0 returns 0 and touches nothing
+ * (src/secp256k1_ecdsa.rs:71-73).  The batch is split into contiguous shards over the pool's devices. */
+int sigops_secp256k1_ecrecover(const uint8_t* sigs, const uint8_t* msgs, size_t n, uint8_t* out_pubkeys,
+                               uint8_t* out_status);
+
+/* secp256r1_ecdsa::ecrecover / ecrecover_single_shader  (src/secp256r1_ecdsa.rs:62-67,216-220). */
+int sigops_secp256r1_ecrecover(const uint8_t* sigs, const uint8_t* msgs, size_t n, uint8_t* out_pubkeys,
+                               uint8_t* out_status);
+
+/* ed25519_eddsa::ecverify / ecverify_single  (src/ed25519_eddsa.rs:67-73,259-264).
+ * sigs: n*64 B, msgs: n*32 B, pks: n*32 B, out_valid: n bytes, each 0 or 1
+ * (the reference returns Vec<bool> from a u32-per-signature buffer, src/ed25519_eddsa.rs:251-254).
+ * An undecodable public key yields 0 (dalek: VerifyingKey::from_bytes fails). */
+int sigops_ed25519_ecverify(const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n,
+                            uint8_t* out_valid);
+
+/* precompute::{secp256k1_bases, secp256r1_bases, ed25519_bases}  (src/precompute.rs:12,36-69).
+ * CPU-only compatibility table: 16 multiples (i+1)*G, coordinates in Montgomery form with
+ * R = 2^(num_limbs*log_limb_size), little-endian log_limb_size-bit limbs; x||y per entry for the secp curves
+ * (src/tests/mod.rs:134-149), x||y||t for ed25519 (src/tests/mod.rs:94-112).
+ * log_limb_size must be in 11..=15 (src/wgsl/mont.wgsl:12,37).  *inout_len: capacity in u32 on entry,
+ * number of u32 written on return (640 / 960 at log_limb_size = 13).  The engine itself never reads
+ * these limbs (its own 32-bit tables are baked into the library). */
+int sigops_precompute_bases(int curve, uint32_t log_limb_size, uint32_t* out, size_t* inout_len);
+
+/* Observability (the reference has none: `timestamp_writes: None`, src/gpu.rs:98).  Milliseconds of the
+ * last host-buffer call, measured with CUDA events on each device's stream; max over the devices used. */
+int sigops_last_timing(double* h2d_ms, double* kernel_ms, double* d2h_ms);
+/* Number of kernels the engine has launched in this process (all devices). */
+uint64_t sigops_kernel_launches(void);
+
+/* Pinned host memory for callers that want zero-staging transfers (replaces the MAP_READ staging buffer of
+ * src/gpu.rs:138-166).  Plain malloc'ed buffers are accepted everywhere too. */
+void* sigops_host_alloc(size_t bytes);
+void sigops_host_free(void* p);
+
+/* Device-resident variants: inputs and outputs already live in the CURRENT CUDA device's memory
+ * (16-byte aligned); the kernel is enqueued on `cuda_stream` (a cudaStream_t; NULL = default stream) and the
+ * call returns without synchronising.  Used by bench.py for the kernel-only figure. */
+int sigops_secp256k1_ecrecover_device(const void* d_sigs, const void* d_msgs, size_t n, void* d_out_pubkeys,
+                                      void* d_out_status, void* cuda_stream);
+int sigops_secp256r1_ecrecover_device(const void* d_sigs, const void* d_msgs, size_t n, void* d_out_pubkeys,
+                                      void* d_out_status, void* cuda_stream);
+int sigops_ed25519_ecverify_device(const void* d_sigs, const void* d_msgs, const void* d_pks, size_t n,
+                                   void* d_out_valid, void* cuda_stream);
+
+/* ---- test and measurement shims (mirror the reference's single-invocation test shaders, src/wgsl/tests/) ---- */
+
+/* Runs device function `op` on n_items independent inputs, one per GPU thread.  Items are fixed-size groups of
+ * 32-bit words (in_words / out_words per item, see SIGOPS_UNIT_* below).  Host pointers. */
+int sigops_test_unit(int op, const uint32_t* in, size_t n_items, uint32_t* out);
+int sigops_test_unit_shape(int op, int* in_words, int* out_words);
+
+/* Integer-pipe micro-benchmark: independent multiply-add chains at full occupancy on every SM of the current
+ * device.  kind 0 = IMAD (32-bit mad.lo), 1 = IMAD.WIDE.U32 (mad.wide), 2 = IMAD.WIDE.U32.X carry chains
+ * (mad.lo.cc/madc.hi.cc), 3 = IADD3 (add), 4 = mixed 1:1 IMAD.WIDE + IADD3.  Returns the measured rate in
+ * instructions (thread-level operations) per second in *ops_per_sec, elapsed GPU time in *ms. */
+int sigops_imad_peak(int kind, int iters, double* ops_per_sec, double* ms);
+
+enum {
+    SIGOPS_UNIT_K1_MUL = 0,    /* in 16 (a,b plain)            out 8  : a*b mod p, canonical          */
+    SIGOPS_UNIT_K1_SQR = 1,    /* in 8                         out 8                                   */
+    SIGOPS_UNIT_K1_ADD = 2,    /* in 16                        out 8                                   */
+    SIGOPS_UNIT_K1_SUB = 3,    /* in 16                        out 8                                   */
+    SIGOPS_UNIT_K1_INV = 4,    /* in 8                         out 8  : a^(p-2)                        */
+    SIGOPS_UNIT_K1_SQRT = 5,   /* in 8                         out 8  : a^((p+1)/4)                    */
+    SIGOPS_UNIT_R1_MUL = 6,    /* plain in, plain out (through Montgomery form)                        */
+    SIGOPS_UNIT_R1_SQR = 7,
+    SIGOPS_UNIT_R1_ADD = 8,
+    SIGOPS_UNIT_R1_SUB = 9,
+    SIGOPS_UNIT_R1_INV = 10,
+    SIGOPS_UNIT_R1_SQRT = 11,
+    SIGOPS_UNIT_ED_MUL = 12,
+    SIGOPS_UNIT_ED_SQR = 13,
+    SIGOPS_UNIT_ED_ADD = 14,
+    SIGOPS_UNIT_ED_SUB = 15,
+    SIGOPS_UNIT_ED_INV = 16,
+    SIGOPS_UNIT_ED_POW_P58 = 17,
+    SIGOPS_UNIT_K1N_MUL = 18,  /* in 16 (a,b < n plain)        out 8  : a*b mod n                      */
+    SIGOPS_UNIT_K1N_INV = 19,  /* in 8                         out 8  : a^-1 mod n                     */
+    SIGOPS_UNIT_R1N_MUL = 20,
+    SIGOPS_UNIT_R1N_INV = 21,
+    SIGOPS_UNIT_EDL_REDUCE512 = 22, /* in 16 (LE 512-bit)      out 8  : mod L                          */
+    SIGOPS_UNIT_SHA512_96 = 23,     /* in 24 (96 bytes)        out 16 : digest bytes                   */
+    SIGOPS_UNIT_K1_GLV = 24,        /* in 8 (k)                out 12 : |k1|[5], |k2|[5], neg1, neg2   */
+    SIGOPS_UNIT_MUL8X8 = 25,        /* in 16                   out 16 : full 512-bit product           */
+    SIGOPS_UNIT_SQR8 = 26,          /* in 8                    out 16                                  */
+    SIGOPS_UNIT_K1_MULPT = 27,      /* in 24 (k, x, y plain)   out 17 : k*(x,y) affine x,y + inf flag  */
+    SIGOPS_UNIT_R1_MULPT = 28,
+    SIGOPS_UNIT_ED_MULPT = 29,      /* in 24 (k, x, y)         out 16 : k*(x,y) affine x,y             */
+    SIGOPS_UNIT_K1_DOUBLE_MUL = 30, /* in 32 (u1,u2,x,y)       out 17 : u1*G + u2*(x,y)                */
+    SIGOPS_UNIT_R1_DOUBLE_MUL = 31,
+    SIGOPS_UNIT_COUNT = 32
+};
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIGOPS_H */

@@ -1,0 +1,636 @@
+"""CPU spec oracle for the wgpu-sigops hot path (TEST INFRASTRUCTURE ONLY).
+
+This file is a plain big-integer restatement of what the reference calls
+"correct" for its three batch operations.  It is imported only by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs;
+the product (libsigops.so) never imports, links or executes anything in
+oracle/.
+
+What it restates (reference file:line, relative to /root/reference):
+
+* ecrecover_k1 / ecrecover_r1 -- the algorithm skeleton of `arkworks_recover`
+  (src/curve_algos/secp256k1_ecdsa.rs:66-120, src/curve_algos/secp256r1_ecdsa.rs:63-117):
+  z, r, s mod n; lift x=r with the requested y parity; u1 = -z/r, u2 = s/r;
+  Q = u1*G + u2*R.  The Fuel compact signature convention (y parity in bit 7 of
+  byte 32) follows `fuel_decode_signature` (src/tests/mod.rs:151-163) and
+  src/wgsl/signature.wgsl:6-21.
+  The *validity rules* are those of the third-party CPU libraries the reference
+  tests compare against (they are not vendored under /root/reference):
+  fuel-crypto 0.49.0 -> secp256k1 0.26.0 / secp256k1-sys 0.8.1 (libsecp256k1
+  `secp256k1_ecdsa_recoverable_signature_parse_compact` + `secp256k1_ecdsa_recover`)
+  for k1 and p256 0.13.2 / ecdsa 0.16.9 `VerifyingKey::recover_from_prehash` for r1
+  (Cargo.lock:711-729,1745-1756,1431-1432,594-595).  Call sites pinned by the
+  reference: src/tests/secp256k1_ecdsa.rs:28-33,94-100, src/tests/secp256r1_ecdsa.rs:29-35,94.
+* ecverify_ed25519 -- ed25519-dalek 2.1.1 `VerifyingKey::verify` (non-strict),
+  curve25519-dalek 4.1.3 decompress / `sqrt_ratio_i`, restated in the reference at
+  src/curve_algos/ed25519_eddsa.rs:49-184 and asserted at src/tests/ed25519_eddsa.rs:26.
+* precompute_bases -- src/precompute.rs:12-69, src/curve_algos/precompute.rs:3-17,
+  src/tests/mod.rs:94-112,134-149 (entry i = (i+1)*G, coordinates * 2^(num_limbs*log_limb_size)
+  mod p, little-endian `log_limb_size`-bit limbs).
+
+PARITY PINNING.  Pinned against: the reference's golden vectors
+(src/curve_algos/secp256k1_ecdsa.rs:136-300 RFC-6979 signature / msg hash / pk = G;
+src/tests/secp256k1_curve.rs:691-741 Strauss-Shamir corner case;
+src/curve_algos/secp256k1_curve.rs:47-68 GLV constants; src/tests/buffers.rs:15-29
+byte order; src/shader.rs:420-428,526-530 constants), RFC 8032 section 7.1 vectors,
+and OpenSSL 3 (`cryptography`) sign/verify on all three curves for valid signatures
+(tests/test_oracle.py, tests/golden/).  NOT pinned by any fixture the reference
+holds: every *rejecting* outcome (r/s range, non-residue x, Q = infinity,
+non-canonical s/A/R, small-order points) -- the reference never tests them
+(SURVEY.md section 4); for those this oracle follows the published algorithms of the
+pinned third-party versions named above.  The Rust toolchain is absent from this
+image, so the reference itself cannot be run here ("parity unpinned" for the
+rejecting classes).
+"""
+from __future__ import annotations
+
+import hashlib
+from typing import List, Optional, Sequence, Tuple
+
+# ----------------------------------------------------------------------------
+# curve parameters (reference: src/moduli.rs:4-50,
+# src/tests/mod.rs:38-64)
+# ----------------------------------------------------------------------------
+
+
+class ShortWeierstrass:
+    def __init__(self, name, p, n, a, b, gx, gy):
+        self.name, self.p, self.n, self.a, self.b, self.gx, self.gy = name, p, n, a, b, gx, gy
+        assert (gy * gy - (gx * gx * gx + a * gx + b)) % p == 0
+        assert p % 4 == 3
+
+
+K1 = ShortWeierstrass(
+    "secp256k1",
+    p=2**256 - 2**32 - 977,
+    n=0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141,
+    a=0,
+    b=7,
+    gx=0x79BE667EF9DCBBAC55A06295CE870B07029BFCDB2DCE28D959F2815B16F81798,
+    gy=0x483ADA7726A3C4655DA4FBFC0E1108A8FD17B448A68554199C47D08FFB10D4B8,
+)
+
+R1 = ShortWeierstrass(
+    "secp256r1",
+    p=0xFFFFFFFF00000001000000000000000000000000FFFFFFFFFFFFFFFFFFFFFFFF,
+    n=0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551,
+    a=0xFFFFFFFF00000001000000000000000000000000FFFFFFFFFFFFFFFFFFFFFFFF - 3,
+    b=0x5AC635D8AA3A93E7B3EBBD55769886BC651D06B0CC53B0F63BCE3C3E27D2604B,
+    gx=0x6B17D1F2E12C4247F8BCE6E563A440F277037D812DEB33A0F4A13945D898C296,
+    gy=0x4FE342E2FE1A7F9B8EE7EB4A7C0F9E162BCE33576B315ECECBB6406837BF51F5,
+)
+
+# GLV constants, src/curve_algos/secp256k1_curve.rs:47-68
+K1_BETA = 0x7AE96A2B657C07106E64479EAC3434E99CF0497512F58995C1396C28719501EE
+K1_LAMBDA = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
+
+ED_P = 2**255 - 19
+ED_L = 2**252 + 27742317777372353535851937790883648493
+ED_D = (-121665 * pow(121666, ED_P - 2, ED_P)) % ED_P
+ED_D2 = 2 * ED_D % ED_P
+ED_SQRT_M1 = pow(2, (ED_P - 1) // 4, ED_P)
+ED_BY = 4 * pow(5, ED_P - 2, ED_P) % ED_P
+ED_BX = 0x216936D3CD6E53FEC0A4E231FDD6DC5C692CC7609525A7B2C9562D608F25D51A
+assert ED_D == 0x52036CEE2B6FFE738CC740797779E89800700A4D4141D8AB75EB4DCA135978A3
+assert ED_D2 == 16295367250680780974490674513165176452449235426866156013048779062215315747161  # src/tests/mod.rs:58-64
+assert ED_SQRT_M1 == 0x2B8324804FC1DF0B2B4D00993DFBD7A72F431806AD2FE478C4EE1B274A0EA0B0
+assert (-ED_BX * ED_BX + ED_BY * ED_BY - 1 - ED_D * ED_BX * ED_BX * ED_BY * ED_BY) % ED_P == 0
+
+# ----------------------------------------------------------------------------
+# short Weierstrass group law (affine, None = infinity).  Complete by case split.
+# ----------------------------------------------------------------------------
+
+Affine = Optional[Tuple[int, int]]
+
+
+def sw_add(c: ShortWeierstrass, P: Affine, Q: Affine) -> Affine:
+    if P is None:
+        return Q
+    if Q is None:
+        return P
+    p = c.p
+    x1, y1 = P
+    x2, y2 = Q
+    if x1 == x2:
+        if (y1 + y2) % p == 0:
+            return None
+        lam = (3 * x1 * x1 + c.a) * pow(2 * y1, p - 2, p) % p
+    else:
+        lam = (y2 - y1) * pow(x2 - x1, p - 2, p) % p
+    x3 = (lam * lam - x1 - x2) % p
+    return x3, (lam * (x1 - x3) - y1) % p
+
+
+def _jac_dbl(c, P):
+    X, Y, Z = P
+    p = c.p
+    if Z == 0 or Y == 0:
+        return (1, 1, 0)
+    S = 4 * X * Y * Y % p
+    M = (3 * X * X + c.a * pow(Z, 4, p)) % p
+    X3 = (M * M - 2 * S) % p
+    Y3 = (M * (S - X3) - 8 * pow(Y, 4, p)) % p
+    return X3, Y3, 2 * Y * Z % p
+
+
+def _jac_add_affine(c, P, Q):
+    if Q is None:
+        return P
+    X1, Y1, Z1 = P
+    p = c.p
+    if Z1 == 0:
+        return (Q[0], Q[1], 1)
+    Z1Z1 = Z1 * Z1 % p
+    U2 = Q[0] * Z1Z1 % p
+    S2 = Q[1] * Z1 * Z1Z1 % p
+    H = (U2 - X1) % p
+    r = (S2 - Y1) % p
+    if H == 0:
+        return _jac_dbl(c, P) if r == 0 else (1, 1, 0)
+    HH = H * H % p
+    HHH = H * HH % p
+    V = X1 * HH % p
+    X3 = (r * r - HHH - 2 * V) % p
+    Y3 = (r * (V - X3) - Y1 * HHH) % p
+    return X3, Y3, Z1 * H % p
+
+
+def _jac_to_affine(c, P) -> Affine:
+    X, Y, Z = P
+    if Z == 0:
+        return None
+    zi = pow(Z, c.p - 2, c.p)
+    return X * zi * zi % c.p, Y * zi * zi * zi % c.p
+
+
+def sw_mul(c: ShortWeierstrass, k: int, P: Affine) -> Affine:
+    """k*P by MSB-first double-and-add in Jacobian coordinates (k >= 0)."""
+    if P is None or k == 0:
+        return None
+    acc = (1, 1, 0)
+    for bit in bin(k)[2:]:
+        acc = _jac_dbl(c, acc)
+        if bit == "1":
+            acc = _jac_add_affine(c, acc, P)
+    return _jac_to_affine(c, acc)
+
+
+def sw_lift_x(c: ShortWeierstrass, x: int, odd: int) -> Affine:
+    """y = (x^3+ax+b)^((p+1)/4), verified; parity chosen.  (src/wgsl/secp256k1_curve.wgsl:258-272
+    computes the same power without the verification.)"""
+    t = (x * x * x + c.a * x + c.b) % c.p
+    y = pow(t, (c.p + 1) // 4, c.p)
+    if y * y % c.p != t:
+        return None
+    if (y & 1) != odd:
+        y = c.p - y
+    return x, y
+
+
+def ecrecover(c: ShortWeierstrass, sig: bytes, msg: bytes) -> Optional[bytes]:
+    """SURVEY.md appendix B.  Returns 64 bytes X||Y (big-endian) or None for InvalidSignature."""
+    assert len(sig) == 64 and len(msg) == 32
+    parity = sig[32] >> 7
+    r = int.from_bytes(sig[0:32], "big")
+    s = int.from_bytes(bytes([sig[32] & 0x7F]) + sig[33:64], "big")
+    z = int.from_bytes(msg, "big") % c.n
+    if r == 0 or r >= c.n or s == 0 or s >= c.n:
+        return None
+    R = sw_lift_x(c, r, parity)
+    if R is None:
+        return None
+    rinv = pow(r, c.n - 2, c.n)
+    u1 = (-rinv * z) % c.n
+    u2 = rinv * s % c.n
+    Q = sw_add(c, sw_mul(c, u1, (c.gx, c.gy)), sw_mul(c, u2, R))
+    if Q is None:
+        return None
+    return Q[0].to_bytes(32, "big") + Q[1].to_bytes(32, "big")
+
+
+def ecrecover_k1(sig: bytes, msg: bytes) -> Optional[bytes]:
+    return ecrecover(K1, sig, msg)
+
+
+def ecrecover_r1(sig: bytes, msg: bytes) -> Optional[bytes]:
+    return ecrecover(R1, sig, msg)
+
+
+def ecdsa_sign(c: ShortWeierstrass, d: int, z_bytes: bytes, k: int, low_s: bool = True) -> bytes:
+    """Fuel-encoded signature (r || s with the y parity of R folded into bit 255 of s).
+    Mirrors what `Signature::sign` / `sign_prehashed` produce for the reference's tests
+    (src/tests/secp256k1_ecdsa.rs:19-27, src/tests/secp256r1_ecdsa.rs:21-30)."""
+    z = int.from_bytes(z_bytes, "big") % c.n
+    Rp = sw_mul(c, k, (c.gx, c.gy))
+    r = Rp[0] % c.n
+    assert r == Rp[0], "x >= n: not encodable in the Fuel format"
+    s = pow(k, c.n - 2, c.n) * (z + r * d) % c.n
+    parity = Rp[1] & 1
+    if low_s and s > c.n // 2:
+        s = c.n - s
+        parity ^= 1
+    assert 0 < s < 2**255 and r != 0
+    sb = bytearray(s.to_bytes(32, "big"))
+    sb[0] |= parity << 7
+    return r.to_bytes(32, "big") + bytes(sb)
+
+
+# ----------------------------------------------------------------------------
+# ed25519 (extended twisted Edwards, a = -1); complete unified formulas
+# ----------------------------------------------------------------------------
+
+EdPoint = Tuple[int, int, int, int]
+ED_IDENT: EdPoint = (0, 1, 1, 0)
+ED_B: EdPoint = (ED_BX, ED_BY, 1, ED_BX * ED_BY % ED_P)
+
+
+def ed_add(P: EdPoint, Q: EdPoint) -> EdPoint:
+    p = ED_P
+    X1, Y1, Z1, T1 = P
+    X2, Y2, Z2, T2 = Q
+    A = (Y1 - X1) * (Y2 - X2) % p
+    B = (Y1 + X1) * (Y2 + X2) % p
+    C = T1 * ED_D2 % p * T2 % p
+    D = 2 * Z1 * Z2 % p
+    E, F, G, H = B - A, D - C, D + C, B + A
+    return E * F % p, G * H % p, F * G % p, E * H % p
+
+
+def ed_mul(k: int, P: EdPoint) -> EdPoint:
+    acc = ED_IDENT
+    for bit in bin(k)[2:] if k else "":
+        acc = ed_add(acc, acc)
+        if bit == "1":
+            acc = ed_add(acc, P)
+    return acc
+
+
+def ed_neg(P: EdPoint) -> EdPoint:
+    return (-P[0]) % ED_P, P[1], P[2], (-P[3]) % ED_P
+
+
+def ed_compress(P: EdPoint) -> bytes:
+    zi = pow(P[2], ED_P - 2, ED_P)
+    x, y = P[0] * zi % ED_P, P[1] * zi % ED_P
+    return (y | ((x & 1) << 255)).to_bytes(32, "little")
+
+
+def ed_sqrt_ratio_i(u: int, v: int) -> Tuple[bool, int]:
+    """src/curve_algos/ed25519_eddsa.rs:160-184 (itself a port of curve25519-dalek)."""
+    p = ED_P
+    v3 = v * v % p * v % p
+    v7 = v3 * v3 % p * v % p
+    r = u * v3 % p * pow(u * v7 % p, (p - 5) // 8, p) % p
+    check = v * r % p * r % p
+    correct = check == u % p
+    flipped = check == (-u) % p
+    flipped_i = check == (-u) * ED_SQRT_M1 % p
+    if flipped or flipped_i:
+        r = r * ED_SQRT_M1 % p
+    if r & 1:
+        r = p - r
+    return (correct or flipped), r
+
+
+def ed_decompress(b: bytes) -> Optional[EdPoint]:
+    """curve25519-dalek 4.1.3 CompressedEdwardsY::decompress (no y < p check);
+    reference restatement: src/curve_algos/ed25519_eddsa.rs:79-102."""
+    sign = b[31] >> 7
+    y = (int.from_bytes(b, "little") & (2**255 - 1)) % ED_P
+    yy = y * y % ED_P
+    ok, x = ed_sqrt_ratio_i((yy - 1) % ED_P, (ED_D * yy + 1) % ED_P)
+    if not ok:
+        return None
+    if sign:
+        x = (-x) % ED_P
+    return x, y, 1, x * y % ED_P
+
+
+def ed_challenge(r_bytes: bytes, a_bytes: bytes, msg: bytes) -> int:
+    """src/curve_algos/ed25519_eddsa.rs:104-118 + Scalar::from_bytes_mod_order_wide."""
+    return int.from_bytes(hashlib.sha512(r_bytes + a_bytes + msg).digest(), "little") % ED_L
+
+
+def ecverify_ed25519(sig: bytes, msg: bytes, pk: bytes) -> bool:
+    """ed25519-dalek 2.1.1 `verify` (non-strict): SURVEY.md appendix B."""
+    assert len(sig) == 64 and len(pk) == 32
+    A = ed_decompress(pk)
+    if A is None:
+        return False
+    s = int.from_bytes(sig[32:], "little")
+    if s >= ED_L:
+        return False
+    k = ed_challenge(sig[:32], pk, msg)
+    Rp = ed_add(ed_mul(s, ED_B), ed_mul(k, ed_neg(A)))
+    return ed_compress(Rp) == sig[:32]
+
+
+def ed25519_expand(seed: bytes) -> Tuple[int, bytes, bytes]:
+    h = hashlib.sha512(seed).digest()
+    a = int.from_bytes(h[:32], "little")
+    a &= (1 << 254) - 8
+    a |= 1 << 254
+    return a, h[32:], ed_compress(ed_mul(a, ED_B))
+
+
+def ed25519_sign(seed: bytes, msg: bytes) -> Tuple[bytes, bytes]:
+    """RFC 8032 5.1.6; returns (signature, public key)."""
+    a, prefix, pk = ed25519_expand(seed)
+    r = int.from_bytes(hashlib.sha512(prefix + msg).digest(), "little") % ED_L
+    Rb = ed_compress(ed_mul(r, ED_B))
+    k = ed_challenge(Rb, pk, msg)
+    s = (r + k * a) % ED_L
+    return Rb + s.to_bytes(32, "little"), pk
+
+
+# ----------------------------------------------------------------------------
+# precompute::*_bases (compatibility tables in the reference's 13-bit limb format)
+# ----------------------------------------------------------------------------
+
+WINDOW_SIZE = 4  # src/precompute.rs:12
+
+
+def calc_num_limbs(log_limb_size: int, p_bitwidth: int = 256) -> int:
+    """multiprecision::utils::calc_num_limbs (used at src/secp256k1_ecdsa.rs:18):
+    smallest l with l*log_limb_size >= bitwidth, plus one when equal (room for the carry)."""
+    l = p_bitwidth // log_limb_size
+    while l * log_limb_size <= p_bitwidth:
+        l += 1
+    return l
+
+
+def to_limbs_le(v: int, num_limbs: int, log_limb_size: int) -> List[int]:
+    mask = (1 << log_limb_size) - 1
+    return [(v >> (log_limb_size * i)) & mask for i in range(num_limbs)]
+
+
+def precompute_bases(curve: str, log_limb_size: int) -> List[int]:
+    num_limbs = calc_num_limbs(log_limb_size)
+    out: List[int] = []
+    if curve in ("secp256k1", "secp256r1"):
+        c = K1 if curve == "secp256k1" else R1
+        R = 1 << (num_limbs * log_limb_size)
+        G = (c.gx, c.gy)
+        cur: Affine = None
+        for _ in range(1 << WINDOW_SIZE):
+            cur = sw_add(c, cur, G)
+            out += to_limbs_le(cur[0] * R % c.p, num_limbs, log_limb_size)
+            out += to_limbs_le(cur[1] * R % c.p, num_limbs, log_limb_size)
+        return out
+    assert curve == "ed25519"
+    R = 1 << (num_limbs * log_limb_size)
+    cur = ED_IDENT
+    for _ in range(1 << WINDOW_SIZE):
+        cur = ed_add(cur, ED_B)
+        zi = pow(cur[2], ED_P - 2, ED_P)
+        x, y = cur[0] * zi % ED_P, cur[1] * zi % ED_P
+        for v in (x, y, x * y % ED_P):
+            out += to_limbs_le(v * R % ED_P, num_limbs, log_limb_size)
+    return out
+
+
+# ----------------------------------------------------------------------------
+# deterministic synthetic inputs: SHA-256 in counter mode
+# ----------------------------------------------------------------------------
+
+GEN_SEED = 0x51600002
+
+
+def prng_bytes(curve: str, index: int, lane: int, nbytes: int = 32, seed: int = GEN_SEED) -> bytes:
+    out = b""
+    ctr = 0
+    while len(out) < nbytes:
+        out += hashlib.sha256(
+            seed.to_bytes(4, "big") + curve.encode() + index.to_bytes(8, "big") + bytes([lane, ctr])
+        ).digest()
+        ctr += 1
+    return out[:nbytes]
+
+
+def gen_ecdsa_valid(c: ShortWeierstrass, index: int, low_s: bool = True):
+    """(sig, msg, expected_pk) -- config-1 style input: random key, message hash, nonce."""
+    while True:
+        d = int.from_bytes(prng_bytes(c.name, index, 0), "big") % (c.n - 1) + 1
+        z = hashlib.sha256(prng_bytes(c.name, index, 1)).digest()
+        k = int.from_bytes(prng_bytes(c.name, index, 2), "big") % (c.n - 1) + 1
+        Rp = sw_mul(c, k, (c.gx, c.gy))
+        if Rp[0] >= c.n:  # probability ~2^-128; keep the generator total
+            index += 1 << 40
+            continue
+        sig = ecdsa_sign(c, d, z, k, low_s=True)
+        if not low_s:
+            # flip to the high-s twin when it is encodable (s < 2^255)
+            s = int.from_bytes(bytes([sig[32] & 0x7F]) + sig[33:], "big")
+            hs = c.n - s
+            if hs < 2**255:
+                sb = bytearray(hs.to_bytes(32, "big"))
+                sb[0] |= ((sig[32] >> 7) ^ 1) << 7
+                sig = sig[:32] + bytes(sb)
+        Q = sw_mul(c, d, (c.gx, c.gy))
+        return sig, z, Q[0].to_bytes(32, "big") + Q[1].to_bytes(32, "big")
+
+
+def gen_ed25519_valid(index: int):
+    seed = prng_bytes("ed25519", index, 0)
+    msg = prng_bytes("ed25519", index, 1)
+    sig, pk = ed25519_sign(seed, msg)
+    return sig, msg, pk
+
+
+def ed_small_order_points() -> List[bytes]:
+    """The 8 points of order dividing 8, canonical encodings."""
+    out = []
+    # find a point of order 8: cofactor-clear complement of a random point
+    i = 0
+    while True:
+        cand = ed_decompress(hashlib.sha256(b"small-order" + bytes([i])).digest())
+        i += 1
+        if cand is None:
+            continue
+        T = ed_mul(ED_L, cand)
+        if ed_compress(ed_mul(4, T)) != ed_compress(ED_IDENT):
+            break
+    cur = ED_IDENT
+    for _ in range(8):
+        out.append(ed_compress(cur))
+        cur = ed_add(cur, T)
+    return out
+
+
+def _ecdsa_sig_bytes(r: int, s: int, parity: int) -> bytes:
+    sb = bytearray((s % 2**255).to_bytes(32, "big"))
+    sb[0] |= parity << 7
+    return (r % 2**256).to_bytes(32, "big") + bytes(sb)
+
+
+def ecdsa_edge_cases(c: ShortWeierstrass, base_index: int = 1 << 32) -> List[Tuple[str, bytes, bytes]]:
+    """(label, sig, msg) triples covering SURVEY.md 8(d) config 3/4 edge classes."""
+    cases = []
+    n, p = c.n, c.p
+    G = (c.gx, c.gy)
+    sig, msg, _ = gen_ecdsa_valid(c, base_index)
+    r = int.from_bytes(sig[:32], "big")
+    s = int.from_bytes(bytes([sig[32] & 0x7F]) + sig[33:], "big")
+    par = sig[32] >> 7
+    cases.append(("valid", sig, msg))
+    cases.append(("wrong_parity", _ecdsa_sig_bytes(r, s, par ^ 1), msg))
+    cases.append(("r_zero", _ecdsa_sig_bytes(0, s, par), msg))
+    cases.append(("s_zero", _ecdsa_sig_bytes(r, 0, par), msg))
+    cases.append(("r_eq_n", _ecdsa_sig_bytes(n, s, par), msg))
+    cases.append(("r_eq_n_plus_1", _ecdsa_sig_bytes(n + 1, s, par), msg))
+    cases.append(("r_max", _ecdsa_sig_bytes(2**256 - 1, s, par), msg))
+    cases.append(("r_eq_p", _ecdsa_sig_bytes(p, s, par), msg))
+    cases.append(("s_max_encodable", _ecdsa_sig_bytes(r, 2**255 - 1, par), msg))
+    cases.append(("s_one", _ecdsa_sig_bytes(r, 1, par), msg))
+    cases.append(("r_one", _ecdsa_sig_bytes(1, s, par), msg))
+    cases.append(("r_n_minus_1", _ecdsa_sig_bytes(n - 1, s, par), msg))
+    cases.append(("all_zero", bytes(64), bytes(32)))
+    cases.append(("all_ff", b"\xff" * 64, b"\xff" * 32))
+    cases.append(("z_zero", sig, bytes(32)))
+    cases.append(("z_eq_n", sig, n.to_bytes(32, "big")))
+    cases.append(("z_gt_n", sig, (n + 5).to_bytes(32, "big")))
+    cases.append(("z_max", sig, b"\xff" * 32))
+    # high-s twin (accepted by both libsecp256k1 recover and p256)
+    sh, mh, _ = gen_ecdsa_valid(c, base_index + 1, low_s=False)
+    cases.append(("high_s", sh, mh))
+    # non-residue x: first r >= 2 for which x^3+ax+b is not a square
+    x = 2
+    while sw_lift_x(c, x, 0) is not None:
+        x += 1
+    cases.append(("x_not_on_curve", _ecdsa_sig_bytes(x, s, par), msg))
+    # R = +G / -G (accumulator meets table entries: P+P and P+(-P) inside the ladder)
+    for lab, parity in (("R_eq_G", c.gy & 1), ("R_eq_negG", (c.gy & 1) ^ 1)):
+        cases.append((lab, _ecdsa_sig_bytes(c.gx, s, parity), msg))
+    # Q = infinity: s*R == z*G.  Take R = k*G, then choose z = s*k.
+    k = int.from_bytes(prng_bytes(c.name, base_index + 2, 2), "big") % (n - 1) + 1
+    Rp = sw_mul(c, k, G)
+    s2 = int.from_bytes(prng_bytes(c.name, base_index + 2, 3), "big") % (2**254) + 1
+    cases.append(("Q_infinity", _ecdsa_sig_bytes(Rp[0], s2, Rp[1] & 1), (s2 * k % n).to_bytes(32, "big")))
+    # u1 == 0 (z = 0) with R = G: Q = (s/r)*G
+    cases.append(("u1_zero_R_eq_G", _ecdsa_sig_bytes(c.gx, s, c.gy & 1), bytes(32)))
+    # u2*R == u1*G exactly (final add is a doubling): R = k*G, want s*k == -z  => z = -s*k
+    cases.append(("final_add_is_double", _ecdsa_sig_bytes(Rp[0], s2, Rp[1] & 1), ((-s2 * k) % n).to_bytes(32, "big")))
+    # small scalars: u2 = 1 (s = r), u2 = 2
+    cases.append(("s_eq_r", _ecdsa_sig_bytes(Rp[0] % 2**255, Rp[0] % 2**255, Rp[1] & 1), msg))
+    if c is K1:
+        # Strauss-Shamir corner case preserved in the reference (src/tests/secp256k1_curve.rs:691-741)
+        # is exercised at the curve level in tests/; here: u2 = lambda (GLV split gives k1=0,k2=1)
+        r3 = Rp[0]
+        s3 = K1_LAMBDA * r3 % n
+        if s3 < 2**255:
+            cases.append(("u2_eq_lambda", _ecdsa_sig_bytes(r3, s3, Rp[1] & 1), msg))
+    return cases
+
+
+def _craft_small_order_accept(a_bytes: bytes, index: int, r_transform=None):
+    """For A of small order find (sig, msg) satisfying the cofactorless equation
+    R = [s]B - [k]A, k = H(R||A||M) (dalek `verify` accepts these).  None if A is not small order."""
+    A = ed_decompress(a_bytes)
+    if A is None or ed_compress(ed_mul(8, A)) != ed_compress(ED_IDENT):
+        return None
+    s_j = int.from_bytes(prng_bytes("ed25519", index, 2), "little") % ED_L
+    m_j = prng_bytes("ed25519", index, 1)
+    sB = ed_mul(s_j, ED_B)
+    for _ in range(256):
+        for t in range(8):
+            Rb = ed_compress(ed_add(sB, ed_mul(t, ed_neg(A))))
+            k = ed_challenge(Rb, a_bytes, m_j)
+            if ed_compress(ed_add(sB, ed_mul(k, ed_neg(A)))) == Rb:
+                return Rb + s_j.to_bytes(32, "little"), m_j
+        m_j = hashlib.sha256(m_j).digest()
+    return None
+
+
+def ed25519_edge_cases(base_index: int = 1 << 32) -> List[Tuple[str, bytes, bytes, bytes]]:
+    """(label, sig, msg, pk) covering SURVEY.md 8(d) config-2 edge classes."""
+    cases = []
+    sig, msg, pk = gen_ed25519_valid(base_index)
+    cases.append(("valid", sig, msg, pk))
+
+    def flip(b: bytes, bit: int) -> bytes:
+        a = bytearray(b)
+        a[bit // 8] ^= 1 << (bit % 8)
+        return bytes(a)
+
+    cases.append(("flip_R", flip(sig, 5), msg, pk))
+    cases.append(("flip_R_sign", flip(sig, 255), msg, pk))
+    cases.append(("flip_s", flip(sig, 256 + 7), msg, pk))
+    cases.append(("flip_A", sig, msg, flip(pk, 3)))
+    cases.append(("flip_A_sign", sig, msg, flip(pk, 255)))
+    cases.append(("flip_M", sig, flip(msg, 100), pk))
+    s = int.from_bytes(sig[32:], "little")
+    cases.append(("s_plus_L", sig[:32] + (s + ED_L).to_bytes(32, "little"), msg, pk))
+    cases.append(("s_eq_L", sig[:32] + ED_L.to_bytes(32, "little"), msg, pk))
+    cases.append(("s_eq_L_minus_1", sig[:32] + (ED_L - 1).to_bytes(32, "little"), msg, pk))
+    cases.append(("s_top_bits", sig[:32] + (s | (7 << 253)).to_bytes(32, "little"), msg, pk))
+    cases.append(("s_zero", sig[:32] + bytes(32), msg, pk))
+    cases.append(("all_zero", bytes(64), bytes(32), bytes(32)))
+    cases.append(("all_ff", b"\xff" * 64, b"\xff" * 32, b"\xff" * 32))
+    # A not on curve
+    y = 2
+    while ed_decompress(y.to_bytes(32, "little")) is not None:
+        y += 1
+    cases.append(("A_not_on_curve", sig, msg, y.to_bytes(32, "little")))
+    # the 8 small-order A: crafted accept (no cofactor check in `verify`) + an unrelated signature
+    small = ed_small_order_points()
+    for j, a_bytes in enumerate(small):
+        got = _craft_small_order_accept(a_bytes, base_index + 10 + j)
+        if got is not None:
+            cases.append((f"small_order_A_{j}_accept", got[0], got[1], a_bytes))
+        cases.append((f"small_order_A_{j}_random", sig, msg, a_bytes))
+    # non-canonical A: y in [p, 2^255) i.e. y = p + t, t in 0..18, both sign bits; dalek reduces y mod p
+    for t in range(19):
+        for signbit in (0, 1):
+            enc = (ED_P + t + (signbit << 255)).to_bytes(32, "little")
+            if ed_decompress(enc) is None:
+                cases.append((f"noncanon_A_{t}_s{signbit}_offcurve", sig, msg, enc))
+                continue
+            got = _craft_small_order_accept(enc, base_index + 40 + 2 * t + signbit)
+            if got is not None:
+                cases.append((f"noncanon_A_{t}_s{signbit}_accept", got[0], got[1], enc))
+            cases.append((f"noncanon_A_{t}_s{signbit}_random", sig, msg, enc))
+    # x = 0 with sign bit 1 (y = 1 identity; y = -1 order 2): encodings dalek accepts for A
+    for yv, lab in ((1, "A_ident_signbit"), (ED_P - 1, "A_order2_signbit")):
+        enc = (yv | (1 << 255)).to_bytes(32, "little")
+        got = _craft_small_order_accept(enc, base_index + 80)
+        if got is not None:
+            cases.append((lab + "_accept", got[0], got[1], enc))
+        cases.append((lab + "_random", sig, msg, enc))
+    # non-canonical R: s = 0, A of order 2, R = identity encoded as y = 1 (canonical, accept when
+    # k is even) versus y = p + 1 (non-canonical: bytes differ from compress(R') => reject)
+    ident_c = ed_compress(ED_IDENT)
+    ident_nc = (ED_P + 1).to_bytes(32, "little")
+    a2 = (ED_P - 1).to_bytes(32, "little")
+    m_j = prng_bytes("ed25519", base_index + 90, 1)
+    for _ in range(256):
+        if ed_challenge(ident_c, a2, m_j) % 2 == 0 and ed_challenge(ident_nc, a2, m_j) % 2 == 0:
+            cases.append(("canon_R_ident_accept", ident_c + bytes(32), m_j, a2))
+            cases.append(("noncanon_R_ident_reject", ident_nc + bytes(32), m_j, a2))
+            break
+        m_j = hashlib.sha256(m_j).digest()
+    # mixed-order key A' = A + T8: the honest signature under A verifies under A' iff k*T8 = 0
+    A = ed_decompress(pk)
+    for j in (1, 4):
+        T = ed_decompress(small[j])
+        cases.append((f"mixed_order_A_{j}", sig, msg, ed_compress(ed_add(A, T))))
+    return cases
+
+
+def selftest() -> None:
+    # golden vector: src/curve_algos/secp256k1_ecdsa.rs:136,161-168,211-214,270-289,300
+    msg = b"A beast can never be as cruel as a human being, so artistically, so picturesquely cruel."
+    z = hashlib.sha256(msg).digest()
+    assert z.hex() == "52840c5594968f39c0d7994330b5638405311580b6f9c1b8b3c1f04ca80db7c3"
+    sig = bytes.fromhex(
+        "46ec716ae185a1d43b537e9ee45e7f178841c9457b5ede4ace9efb585b8ad59f"
+        "0131dd08f04930d2771de52d2e6aa3f7d12da172ba8af87e963921cd7ed39182"
+    )
+    pk = ecrecover_k1(sig, z)
+    assert pk == K1.gx.to_bytes(32, "big") + K1.gy.to_bytes(32, "big")
+    lg = sw_mul(K1, K1_LAMBDA, (K1.gx, K1.gy))
+    assert lg == (K1_BETA * K1.gx % K1.p, K1.gy)
+
+
+if __name__ == "__main__":
+    selftest()
+    print("oracle selftest ok")

@@ -1,0 +1,62 @@
+// Host simulation of the device code (TEST INFRASTRUCTURE ONLY).
+//
+// Compiles the very same headers the CUDA kernels are built from with a plain C++ compiler; the inline-PTX bodies
+// are replaced by their portable uint64_t twins (arith.cuh, SG_PTX == 0).  This lets the `-m "not gpu"` tests check
+// all the host-visible logic -- reductions, addition chains, group law corner cases, recoding, GLV split, the
+// fused per-signature functions -- against the oracle without a GPU.  It is never linked into libsigops.so.
+#include <cstring>
+#include <vector>
+#include "../../wgpu-sigops_b200/csrc/kernels.cuh"
+
+using namespace sigops;
+
+extern "C" {
+
+int hostsim_unit(int op, const uint32_t* in, size_t n, uint32_t* out) {
+    int in_w, out_w;
+    unit_shape(op, in_w, out_w);
+    std::vector<Q4> scratch(kEdTabChunks);
+    TabRef tab{scratch.data(), 1};
+    for (size_t i = 0; i < n; i++) {
+        u32 a[32], r[17];
+        for (int j = 0; j < 32; j++) a[j] = j < in_w ? in[i * in_w + j] : 0u;
+        for (int j = 0; j < 17; j++) r[j] = 0;
+        unit_dispatch(op, r, a, tab, k1_gtab, r1_gtab, ed_btab);
+        for (int j = 0; j < out_w; j++) out[i * out_w + j] = r[j];
+    }
+    return 0;
+}
+
+int hostsim_unit_shape(int op, int* in_w, int* out_w) {
+    unit_shape(op, *in_w, *out_w);
+    return 0;
+}
+
+int hostsim_ecrecover(int curve, const uint8_t* sigs, const uint8_t* msgs, size_t n, uint8_t* out, uint8_t* status) {
+    std::vector<Q4> scratch(kSwTabChunks);
+    TabRef tab{scratch.data(), 1};
+    for (size_t i = 0; i < n; i++) {
+        u32 sig_w[16], msg_w[8], out_w[16];
+        memcpy(sig_w, sigs + 64 * i, 64);
+        memcpy(msg_w, msgs + 32 * i, 32);
+        u32 st = curve == 0 ? sw_ecrecover_one<CurveK1>(out_w, sig_w, msg_w, tab, k1_gtab)
+                            : sw_ecrecover_one<CurveR1>(out_w, sig_w, msg_w, tab, r1_gtab);
+        memcpy(out + 64 * i, out_w, 64);
+        if (status) status[i] = (uint8_t)st;
+    }
+    return 0;
+}
+
+int hostsim_ed25519_verify(const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n, uint8_t* valid) {
+    std::vector<Q4> scratch(kEdTabChunks);
+    TabRef tab{scratch.data(), 1};
+    for (size_t i = 0; i < n; i++) {
+        u32 sig_w[16], msg_w[8], pk_w[8];
+        memcpy(sig_w, sigs + 64 * i, 64);
+        memcpy(msg_w, msgs + 32 * i, 32);
+        memcpy(pk_w, pks + 32 * i, 32);
+        valid[i] = (uint8_t)ed_verify_one(sig_w, msg_w, pk_w, tab, ed_btab);
+    }
+    return 0;
+}
+}

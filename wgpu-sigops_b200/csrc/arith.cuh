@@ -1,0 +1,434 @@
+// 256-bit multi-precision primitives on 8 x 32-bit little-endian limbs.
+//
+// Replaces the reference's 20 x 13-bit limb WGSL bigint layer
+// (src/wgsl/bigint.wgsl:13-246, src/wgsl/ff.wgsl:122-138 `bigint_mul`,
+// src/wgsl/mont.wgsl:5-70 `mont_mul`) with full 32-bit limbs and PTX carry chains
+// (`add.cc/addc.cc`, `mad.lo.cc/madc.hi.cc`).  ptxas fuses each lo/hi pair into one
+// IMAD.WIDE.U32(.X) with the carry in a predicate register (see profiles/sass_*.txt).
+//
+// Every primitive has two bodies: inline PTX under __CUDA_ARCH__ (the product) and a
+// portable uint64_t body used only when the same headers are compiled for the host by
+// tests/hostsim (logic tests without a GPU) and by the CPU-only precompute_bases table
+// builder.  The product's compute entry points never run the portable bodies.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SG_HD __host__ __device__ __forceinline__
+#define SG_D __device__ __forceinline__
+#else
+#define SG_HD inline
+#define SG_D inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define SG_PTX 1
+#else
+#define SG_PTX 0
+#endif
+
+namespace sigops {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+// r = a + b, returns carry out
+SG_HD u32 add8(u32* r, const u32* a, const u32* b) {
+    u32 c;
+#if SG_PTX
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+#else
+    u64 t = 0;
+    for (int i = 0; i < 8; i++) {
+        t += (u64)a[i] + b[i];
+        r[i] = (u32)t;
+        t >>= 32;
+    }
+    c = (u32)t;
+#endif
+    return c;
+}
+
+// r = a - b, returns borrow out (1 if a < b)
+SG_HD u32 sub8(u32* r, const u32* a, const u32* b) {
+    u32 c;
+#if SG_PTX
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    c &= 1u;  // subc.u32 x,0,0 yields 0 or 0xffffffff
+#else
+    u64 bw = 0;
+    for (int i = 0; i < 8; i++) {
+        u64 t = (u64)a[i] - b[i] - bw;
+        r[i] = (u32)t;
+        bw = (t >> 32) & 1;
+    }
+    c = (u32)bw;
+#endif
+    return c;
+}
+
+// r += (lo, hi) at limbs 0,1 with carry propagated through all 8 limbs; returns carry out
+SG_HD u32 add8_small(u32* r, u32 lo, u32 hi) {
+    u32 c;
+#if SG_PTX
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, %10;\n\t"
+        "addc.cc.u32 %2, %2, 0;\n\t"
+        "addc.cc.u32 %3, %3, 0;\n\t"
+        "addc.cc.u32 %4, %4, 0;\n\t"
+        "addc.cc.u32 %5, %5, 0;\n\t"
+        "addc.cc.u32 %6, %6, 0;\n\t"
+        "addc.cc.u32 %7, %7, 0;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(c)
+        : "r"(lo), "r"(hi));
+#else
+    u64 t = (u64)r[0] + lo;
+    r[0] = (u32)t;
+    t = (t >> 32) + r[1] + hi;
+    r[1] = (u32)t;
+    t >>= 32;
+    for (int i = 2; i < 8; i++) {
+        t += r[i];
+        r[i] = (u32)t;
+        t >>= 32;
+    }
+    c = (u32)t;
+#endif
+    return c;
+}
+
+// r -= (lo, hi) at limbs 0,1 with borrow propagated; returns borrow out
+SG_HD u32 sub8_small(u32* r, u32 lo, u32 hi) {
+    u32 c;
+#if SG_PTX
+    asm("sub.cc.u32 %0, %0, %9;\n\t"
+        "subc.cc.u32 %1, %1, %10;\n\t"
+        "subc.cc.u32 %2, %2, 0;\n\t"
+        "subc.cc.u32 %3, %3, 0;\n\t"
+        "subc.cc.u32 %4, %4, 0;\n\t"
+        "subc.cc.u32 %5, %5, 0;\n\t"
+        "subc.cc.u32 %6, %6, 0;\n\t"
+        "subc.cc.u32 %7, %7, 0;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(c)
+        : "r"(lo), "r"(hi));
+    c &= 1u;
+#else
+    u64 t = (u64)r[0] - lo;
+    r[0] = (u32)t;
+    u64 bw = (t >> 32) & 1;
+    t = (u64)r[1] - hi - bw;
+    r[1] = (u32)t;
+    bw = (t >> 32) & 1;
+    for (int i = 2; i < 8; i++) {
+        t = (u64)r[i] - bw;
+        r[i] = (u32)t;
+        bw = (t >> 32) & 1;
+    }
+    c = (u32)bw;
+#endif
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------
+// wide multiply-accumulate rows.  acc[0..2n) += {x0,..,x(n-1)} * b, the n wide products landing on the
+// aligned limb pairs (0,1),(2,3),...; one carry chain; returns the carry out of the top limb.
+// ---------------------------------------------------------------------------------------
+SG_HD u32 mad_row4(u32* acc, u32 x0, u32 x1, u32 x2, u32 x3, u32 b) {
+    u32 c;
+#if SG_PTX
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
+          "=r"(c)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
+#else
+    const u32 x[4] = {x0, x1, x2, x3};
+    u64 cy = 0;
+    for (int j = 0; j < 4; j++) {
+        u64 cur = ((u64)acc[2 * j + 1] << 32) | acc[2 * j];
+        u64 prod = (u64)x[j] * b;
+        u64 s = cur + prod;
+        u64 c1 = s < cur;
+        u64 s2 = s + cy;
+        u64 c2 = s2 < s;
+        acc[2 * j] = (u32)s2;
+        acc[2 * j + 1] = (u32)(s2 >> 32);
+        cy = c1 + c2;
+    }
+    c = (u32)cy;
+#endif
+    return c;
+}
+
+SG_HD u32 mad_row3(u32* acc, u32 x0, u32 x1, u32 x2, u32 b) {
+    u32 c;
+#if SG_PTX
+    asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+        "addc.u32 %6, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "=r"(c)
+        : "r"(x0), "r"(x1), "r"(x2), "r"(b));
+#else
+    const u32 x[3] = {x0, x1, x2};
+    u64 cy = 0;
+    for (int j = 0; j < 3; j++) {
+        u64 cur = ((u64)acc[2 * j + 1] << 32) | acc[2 * j];
+        u64 prod = (u64)x[j] * b;
+        u64 s = cur + prod;
+        u64 c1 = s < cur;
+        u64 s2 = s + cy;
+        u64 c2 = s2 < s;
+        acc[2 * j] = (u32)s2;
+        acc[2 * j + 1] = (u32)(s2 >> 32);
+        cy = c1 + c2;
+    }
+    c = (u32)cy;
+#endif
+    return c;
+}
+
+SG_HD u32 mad_row2(u32* acc, u32 x0, u32 x1, u32 b) {
+    u32 c;
+#if SG_PTX
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(c)
+        : "r"(x0), "r"(x1), "r"(b));
+#else
+    const u32 x[2] = {x0, x1};
+    u64 cy = 0;
+    for (int j = 0; j < 2; j++) {
+        u64 cur = ((u64)acc[2 * j + 1] << 32) | acc[2 * j];
+        u64 prod = (u64)x[j] * b;
+        u64 s = cur + prod;
+        u64 c1 = s < cur;
+        u64 s2 = s + cy;
+        u64 c2 = s2 < s;
+        acc[2 * j] = (u32)s2;
+        acc[2 * j + 1] = (u32)(s2 >> 32);
+        cy = c1 + c2;
+    }
+    c = (u32)cy;
+#endif
+    return c;
+}
+
+SG_HD u32 mad_row1(u32* acc, u32 x0, u32 b) {
+    u32 c;
+#if SG_PTX
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "=r"(c)
+        : "r"(x0), "r"(b));
+#else
+    u64 cur = ((u64)acc[1] << 32) | acc[0];
+    u64 s = cur + (u64)x0 * b;
+    c = (u32)(s < cur);
+    acc[0] = (u32)s;
+    acc[1] = (u32)(s >> 32);
+#endif
+    return c;
+}
+
+// (lo,hi) = x*b written to acc[0],acc[1] (no accumulate)
+SG_HD void mul_wide(u32* acc, u32 x, u32 b) {
+#if SG_PTX
+    asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=r"(acc[0]), "=r"(acc[1]) : "r"(x), "r"(b));
+#else
+    u64 p = (u64)x * b;
+    acc[0] = (u32)p;
+    acc[1] = (u32)(p >> 32);
+#endif
+}
+
+// r[0..16) = e[0..16) + (o[0..15) << 32): merge of the even/odd column accumulators
+SG_HD void merge_even_odd(u32* r, const u32* e, const u32* o) {
+#if SG_PTX
+    r[0] = e[0];
+    asm("add.cc.u32 %0, %15, %30;\n\t"
+        "addc.cc.u32 %1, %16, %31;\n\t"
+        "addc.cc.u32 %2, %17, %32;\n\t"
+        "addc.cc.u32 %3, %18, %33;\n\t"
+        "addc.cc.u32 %4, %19, %34;\n\t"
+        "addc.cc.u32 %5, %20, %35;\n\t"
+        "addc.cc.u32 %6, %21, %36;\n\t"
+        "addc.cc.u32 %7, %22, %37;\n\t"
+        "addc.cc.u32 %8, %23, %38;\n\t"
+        "addc.cc.u32 %9, %24, %39;\n\t"
+        "addc.cc.u32 %10, %25, %40;\n\t"
+        "addc.cc.u32 %11, %26, %41;\n\t"
+        "addc.cc.u32 %12, %27, %42;\n\t"
+        "addc.cc.u32 %13, %28, %43;\n\t"
+        "addc.u32 %14, %29, %44;"
+        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(e[8]), "r"(e[9]), "r"(e[10]),
+          "r"(e[11]), "r"(e[12]), "r"(e[13]), "r"(e[14]), "r"(e[15]), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+          "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]),
+          "r"(o[13]), "r"(o[14]));
+#else
+    r[0] = e[0];
+    u64 t = 0;
+    for (int k = 1; k < 16; k++) {
+        t += (u64)e[k] + o[k - 1];
+        r[k] = (u32)t;
+        t >>= 32;
+    }
+#endif
+}
+
+// r[0..16) = a[0..8) * b[0..8): 64 wide MACs on even/odd column accumulators (carry-outs always land on a
+// fresh limb, see DESIGN.md "field multiplication").
+SG_HD void mul8x8(u32* r, const u32* a, const u32* b) {
+    u32 e[16], o[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        e[i] = 0;
+        o[i] = 0;
+    }
+    // row 0: plain products
+    mul_wide(e + 0, a[0], b[0]);
+    mul_wide(e + 2, a[2], b[0]);
+    mul_wide(e + 4, a[4], b[0]);
+    mul_wide(e + 6, a[6], b[0]);
+    mul_wide(o + 0, a[1], b[0]);
+    mul_wide(o + 2, a[3], b[0]);
+    mul_wide(o + 4, a[5], b[0]);
+    mul_wide(o + 6, a[7], b[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i += 2) {
+        // odd row i: a_even*b_i -> odd columns (o index i-1..i+6, second use: carry to fresh o[i+7]);
+        //            a_odd*b_i  -> even columns (e index i+1..i+8, top pair fresh)
+        o[i + 7] = mad_row4(o + i - 1, a[0], a[2], a[4], a[6], b[i]);
+        mad_row4(e + i + 1, a[1], a[3], a[5], a[7], b[i]);
+        if (i + 1 < 8) {
+            // even row i+1: a_even*b -> even columns (e index i+1..i+8, second use: carry to fresh e[i+9]);
+            //               a_odd*b  -> odd columns (o index i+1..i+8, top pair holds only the carry limb)
+            e[i + 9] = mad_row4(e + i + 1, a[0], a[2], a[4], a[6], b[i + 1]);
+            mad_row4(o + i + 1, a[1], a[3], a[5], a[7], b[i + 1]);
+        }
+    }
+    merge_even_odd(r, e, o);
+}
+
+// r[0..16) += sum a_i^2 * 2^(64 i)
+SG_HD void mad_diag8(u32* r, const u32* a) {
+#if SG_PTX
+    asm("mad.lo.cc.u32 %0, %16, %16, %0;\n\t"
+        "madc.hi.cc.u32 %1, %16, %16, %1;\n\t"
+        "madc.lo.cc.u32 %2, %17, %17, %2;\n\t"
+        "madc.hi.cc.u32 %3, %17, %17, %3;\n\t"
+        "madc.lo.cc.u32 %4, %18, %18, %4;\n\t"
+        "madc.hi.cc.u32 %5, %18, %18, %5;\n\t"
+        "madc.lo.cc.u32 %6, %19, %19, %6;\n\t"
+        "madc.hi.cc.u32 %7, %19, %19, %7;\n\t"
+        "madc.lo.cc.u32 %8, %20, %20, %8;\n\t"
+        "madc.hi.cc.u32 %9, %20, %20, %9;\n\t"
+        "madc.lo.cc.u32 %10, %21, %21, %10;\n\t"
+        "madc.hi.cc.u32 %11, %21, %21, %11;\n\t"
+        "madc.lo.cc.u32 %12, %22, %22, %12;\n\t"
+        "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
+        "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
+        "madc.hi.u32 %15, %23, %23, %15;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+          "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+#else
+    u64 cy = 0;
+    for (int j = 0; j < 8; j++) {
+        u64 cur = ((u64)r[2 * j + 1] << 32) | r[2 * j];
+        u64 prod = (u64)a[j] * a[j];
+        u64 s = cur + prod;
+        u64 c1 = s < cur;
+        u64 s2 = s + cy;
+        u64 c2 = s2 < s;
+        r[2 * j] = (u32)s2;
+        r[2 * j + 1] = (u32)(s2 >> 32);
+        cy = c1 + c2;
+    }
+#endif
+}
+
+// r[0..16) = a^2: 28 cross products (doubled by a funnel shift) + 8 diagonal squares accumulated on top.
+SG_HD void sqr8(u32* r, const u32* a) {
+    u32 e[16], o[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        e[i] = 0;
+        o[i] = 0;
+    }
+    // row 0 (a0 * a1..a7): odd columns 1,3,5,7 -> o[0..8); even columns 2,4,6 -> e[2..8)
+    mul_wide(o + 0, a[1], a[0]);
+    mul_wide(o + 2, a[3], a[0]);
+    mul_wide(o + 4, a[5], a[0]);
+    mul_wide(o + 6, a[7], a[0]);
+    mul_wide(e + 2, a[2], a[0]);
+    mul_wide(e + 4, a[4], a[0]);
+    mul_wide(e + 6, a[6], a[0]);
+    // row 1 (a1 * a2..a7): even columns 4,6,8 -> e[4..10); odd columns 3,5,7 -> o[2..8) carry -> o[8]
+    mad_row3(e + 4, a[3], a[5], a[7], a[1]);
+    o[8] = mad_row3(o + 2, a[2], a[4], a[6], a[1]);
+    // row 2 (a2 * a3..a7): odd columns 5,7,9 -> o[4..10); even columns 6,8 -> e[6..10) carry -> e[10]
+    mad_row3(o + 4, a[3], a[5], a[7], a[2]);
+    e[10] = mad_row2(e + 6, a[4], a[6], a[2]);
+    // row 3 (a3 * a4..a7): even columns 8,10 -> e[8..12); odd columns 7,9 -> o[6..10) carry -> o[10]
+    mad_row2(e + 8, a[5], a[7], a[3]);
+    o[10] = mad_row2(o + 6, a[4], a[6], a[3]);
+    // row 4 (a4 * a5..a7): odd columns 9,11 -> o[8..12); even column 10 -> e[10..12) carry -> e[12]
+    mad_row2(o + 8, a[5], a[7], a[4]);
+    e[12] = mad_row1(e + 10, a[6], a[4]);
+    // row 5 (a5 * a6,a7): even column 12 -> e[12..14); odd column 11 -> o[10..12) carry -> o[12]
+    mad_row1(e + 12, a[7], a[5]);
+    o[12] = mad_row1(o + 10, a[6], a[5]);
+    // row 6 (a6 * a7): odd column 13 -> o[12..14)
+    mad_row1(o + 12, a[7], a[6]);
+    u32 t[16];
+    merge_even_odd(t, e, o);
+    // double the cross terms
+#pragma unroll
+    for (int k = 15; k > 0; k--) r[k] = (t[k] << 1) | (t[k - 1] >> 31);
+    r[0] = t[0] << 1;
+    // add the diagonal a_i^2 at limb pairs (2i, 2i+1): one 16-instruction chain (no carry out: a^2 < 2^512)
+    mad_diag8(r, a);
+}
+
+}  // namespace sigops

@@ -1,0 +1,432 @@
+// Short-Weierstrass group law (Jacobian coordinates) and the fused ECDSA public-key recovery for
+// secp256k1 and secp256r1: one signature per thread, everything between the input bytes and the output
+// bytes stays in registers / the per-thread table.
+//
+// Replaces the reference's five-stage pipeline (src/secp256k1_ecdsa.rs:61-213, src/secp256r1_ecdsa.rs:62-214;
+// stages src/wgsl/main/secp256k1_ecdsa_main_0..4.wgsl) and its device functions:
+//   src/wgsl/secp256k1_ecdsa.wgsl:7-130   `secp256k1_ecrecover_0` / `secp256k1_ecrecover`
+//   src/wgsl/secp256k1_curve.wgsl:26-111  projective add-2007-bl / dbl-2007-bl (incomplete: "unsafe")
+//   src/wgsl/secp256r1_curve.wgsl:34-146  RCB-2015 complete add / dbl
+//   src/wgsl/secp256k1_curve.wgsl:277-294,388-447  `projective_mul` (double-and-add), `projective_fixed_mul`
+//   src/wgsl/secp_curve_utils.wgsl:1-30   `projective_to_affine_non_mont`
+//   src/wgsl/signature.wgsl:6-21          `decode_signature`
+// Differences by design: Jacobian formulas with explicit handling of infinity / P == Q / P == -Q (the reference's
+// formulas are wrong there); ONE interleaved Strauss-Shamir pass with fixed signed windows
+// (GLV-split into four 128-bit streams on secp256k1) instead of two independent scalar multiplications; and the
+// validity checks of the CPU libraries the reference is tested against (r, s range; x not on curve; Q = infinity),
+// reported per signature.
+#pragma once
+#include "scalar.cuh"
+
+namespace sigops {
+
+struct alignas(16) Q4 {
+    u32 x, y, z, w;
+};
+
+// Per-thread scratch table in 16-byte chunks, interleaved across threads: chunk q of this thread is base[q*stride].
+// Adjacent lanes touch adjacent 16-byte slots whatever entry each lane selects (coalesced in global memory,
+// conflict-free in shared memory).
+struct TabRef {
+    Q4* base;
+    u32 stride;
+};
+
+SG_HD void tab_store_fe(const TabRef& t, int chunk, const Fe& a) {
+    Q4 lo = {a.v[0], a.v[1], a.v[2], a.v[3]}, hi = {a.v[4], a.v[5], a.v[6], a.v[7]};
+    t.base[(size_t)chunk * t.stride] = lo;
+    t.base[(size_t)(chunk + 1) * t.stride] = hi;
+}
+SG_HD void tab_load_fe(Fe& a, const TabRef& t, int chunk) {
+    Q4 lo = t.base[(size_t)chunk * t.stride], hi = t.base[(size_t)(chunk + 1) * t.stride];
+    a.v[0] = lo.x;
+    a.v[1] = lo.y;
+    a.v[2] = lo.z;
+    a.v[3] = lo.w;
+    a.v[4] = hi.x;
+    a.v[5] = hi.y;
+    a.v[6] = hi.z;
+    a.v[7] = hi.w;
+}
+
+struct JacPoint {
+    Fe X, Y, Z;
+    bool inf;
+};
+
+struct CurveK1 {
+    typedef FpK1 F;
+    typedef Sc<ModK1N> S;
+    static constexpr bool kGlv = true;
+    static constexpr bool kAIsZero = true;
+    // t = x^3 + 7
+    static SG_HD void rhs(Fe& t, const Fe& x) {
+        Fe x2, b;
+        F::sqr(x2, x);
+        F::mul(t, x2, x);
+        F::set_small(b, 7u);
+        F::add(t, t, b);
+    }
+    static SG_HD void mul_beta(Fe& r, const Fe& a) {
+        const Fe beta = {SG_K1_BETA};
+        F::mul(r, a, beta);
+    }
+};
+
+struct CurveR1 {
+    typedef FpR1 F;
+    typedef Sc<ModR1N> S;
+    static constexpr bool kGlv = false;
+    static constexpr bool kAIsZero = false;  // a = -3
+    // t = x^3 - 3x + b   (Montgomery domain)
+    static SG_HD void rhs(Fe& t, const Fe& x) {
+        const Fe b = {SG_R1_B_MONT};
+        Fe x2, x3;
+        F::sqr(x2, x);
+        F::mul(t, x2, x);
+        F::dbl(x3, x);
+        F::add(x3, x3, x);
+        F::sub(t, t, x3);
+        F::add(t, t, b);
+    }
+    static SG_HD void mul_beta(Fe& r, const Fe& a) { r = a; }
+};
+
+// P <- 2P.  a = 0: dbl-2009-l (2M + 5S);  a = -3: dbl-2001-b (3M + 5S).  No point of order 2 on either curve.
+template <class C>
+SG_HD void jac_dbl(JacPoint& P) {
+    typedef typename C::F F;
+    if (P.inf) return;
+    if (C::kAIsZero) {
+        Fe A, B, Cc, D, E, Fq, t;
+        F::sqr(A, P.X);
+        F::sqr(B, P.Y);
+        F::sqr(Cc, B);
+        F::add(t, P.X, B);
+        F::sqr(t, t);
+        F::sub(t, t, A);
+        F::sub(t, t, Cc);
+        F::dbl(D, t);
+        F::dbl(E, A);
+        F::add(E, E, A);
+        F::sqr(Fq, E);
+        F::mul(P.Z, P.Y, P.Z);
+        F::dbl(P.Z, P.Z);
+        F::dbl(t, D);
+        F::sub(P.X, Fq, t);
+        F::sub(t, D, P.X);
+        F::mul(t, E, t);
+        F::dbl(Cc, Cc);
+        F::dbl(Cc, Cc);
+        F::dbl(Cc, Cc);
+        F::sub(P.Y, t, Cc);
+    } else {
+        Fe delta, gamma, beta, alpha, t, u;
+        F::sqr(delta, P.Z);
+        F::sqr(gamma, P.Y);
+        F::mul(beta, P.X, gamma);
+        F::sub(t, P.X, delta);
+        F::add(u, P.X, delta);
+        F::mul(alpha, t, u);
+        F::dbl(t, alpha);
+        F::add(alpha, alpha, t);
+        F::add(t, P.Y, P.Z);
+        F::sqr(t, t);
+        F::sub(t, t, gamma);
+        F::sub(P.Z, t, delta);
+        F::sqr(t, alpha);
+        F::dbl(beta, beta);
+        F::dbl(beta, beta);  // 4*beta
+        F::dbl(u, beta);     // 8*beta
+        F::sub(P.X, t, u);
+        F::sub(t, beta, P.X);
+        F::mul(t, alpha, t);
+        F::sqr(gamma, gamma);
+        F::dbl(gamma, gamma);
+        F::dbl(gamma, gamma);
+        F::dbl(gamma, gamma);
+        F::sub(P.Y, t, gamma);
+    }
+}
+
+// shared tail of the two additions: given U1,S1 (of P), H = U2-U1, r = S2-S1 and Zm = Z1*Z2 (or Z1), H != 0
+template <class F>
+SG_HD void jac_add_tail(JacPoint& P, const Fe& U1, const Fe& S1, const Fe& H, const Fe& r, const Fe& Zm) {
+    Fe HH, HHH, V, t;
+    F::sqr(HH, H);
+    F::mul(HHH, H, HH);
+    F::mul(V, U1, HH);
+    F::sqr(t, r);
+    F::sub(t, t, HHH);
+    F::sub(t, t, V);
+    F::sub(P.X, t, V);
+    F::sub(t, V, P.X);
+    F::mul(t, r, t);
+    F::mul(HHH, S1, HHH);
+    F::sub(P.Y, t, HHH);
+    F::mul(P.Z, Zm, H);
+}
+
+// P <- P + (x2, y2) with an affine second operand that is never infinity (8M + 3S)
+template <class C>
+SG_HD void jac_madd(JacPoint& P, const Fe& x2, const Fe& y2) {
+    typedef typename C::F F;
+    if (P.inf) {
+        P.X = x2;
+        P.Y = y2;
+        F::set_one(P.Z);
+        P.inf = false;
+        return;
+    }
+    Fe Z1Z1, U2, S2, H, r;
+    F::sqr(Z1Z1, P.Z);
+    F::mul(U2, x2, Z1Z1);
+    F::mul(S2, P.Z, Z1Z1);
+    F::mul(S2, y2, S2);
+    F::sub(H, U2, P.X);
+    F::sub(r, S2, P.Y);
+    if (F::is_zero(H)) {
+        if (F::is_zero(r))
+            jac_dbl<C>(P);
+        else
+            P.inf = true;
+        return;
+    }
+    Fe U1 = P.X, S1 = P.Y, Zm = P.Z;
+    jac_add_tail<F>(P, U1, S1, H, r, Zm);
+}
+
+// P <- P + Q with Q = (X2, Y2, Z2) Jacobian, never infinity (12M + 4S)
+template <class C>
+SG_HD void jac_add(JacPoint& P, const Fe& X2, const Fe& Y2, const Fe& Z2) {
+    typedef typename C::F F;
+    if (P.inf) {
+        P.X = X2;
+        P.Y = Y2;
+        P.Z = Z2;
+        P.inf = false;
+        return;
+    }
+    Fe Z1Z1, Z2Z2, U1, U2, S1, S2, H, r, Zm;
+    F::sqr(Z1Z1, P.Z);
+    F::sqr(Z2Z2, Z2);
+    F::mul(U1, P.X, Z2Z2);
+    F::mul(U2, X2, Z1Z1);
+    F::mul(S1, Z2, Z2Z2);
+    F::mul(S1, P.Y, S1);
+    F::mul(S2, P.Z, Z1Z1);
+    F::mul(S2, Y2, S2);
+    F::sub(H, U2, U1);
+    F::sub(r, S2, S1);
+    if (F::is_zero(H)) {
+        if (F::is_zero(r))
+            jac_dbl<C>(P);
+        else
+            P.inf = true;
+        return;
+    }
+    F::mul(Zm, P.Z, Z2);
+    jac_add_tail<F>(P, U1, S1, H, r, Zm);
+}
+
+// table entry e (0-based: (e+1)*R) occupies chunks [6e, 6e+6): X, Y, Z
+SG_HD void tab_store_jac(const TabRef& t, int e, const JacPoint& P) {
+    tab_store_fe(t, 6 * e + 0, P.X);
+    tab_store_fe(t, 6 * e + 2, P.Y);
+    tab_store_fe(t, 6 * e + 4, P.Z);
+}
+
+static constexpr int kSwTabEntries = 8;                      // {1..8} * R, signed 4-bit windows
+static constexpr int kSwTabChunks = kSwTabEntries * 6;       // 16-byte chunks per thread (768 B)
+
+// Build {1..8}*R from affine R = (x, y): 4 doublings + 3 mixed additions
+template <class C>
+SG_HD void sw_build_table(const TabRef& tab, const Fe& x, const Fe& y) {
+    typedef typename C::F F;
+    JacPoint P1, P2, P3, P4, T;
+    P1.X = x;
+    P1.Y = y;
+    F::set_one(P1.Z);
+    P1.inf = false;
+    tab_store_jac(tab, 0, P1);
+    P2 = P1;
+    jac_dbl<C>(P2);
+    tab_store_jac(tab, 1, P2);
+    P3 = P2;
+    jac_madd<C>(P3, x, y);
+    tab_store_jac(tab, 2, P3);
+    P4 = P2;
+    jac_dbl<C>(P4);
+    tab_store_jac(tab, 3, P4);
+    T = P4;
+    jac_madd<C>(T, x, y);
+    tab_store_jac(tab, 4, T);  // 5R
+    T = P3;
+    jac_dbl<C>(T);
+    tab_store_jac(tab, 5, T);  // 6R
+    jac_madd<C>(T, x, y);
+    tab_store_jac(tab, 6, T);  // 7R
+    T = P4;
+    jac_dbl<C>(T);
+    tab_store_jac(tab, 7, T);  // 8R
+}
+
+// acc += sign(d) * |d| * R (optionally mapped through the endomorphism (x,y) -> (beta*x, y))
+template <class C>
+SG_HD void sw_add_from_table(JacPoint& acc, const TabRef& tab, int d, bool flip, bool endo) {
+    typedef typename C::F F;
+    if (d == 0) return;
+    int e = (d < 0 ? -d : d) - 1;
+    Fe X, Y, Z;
+    tab_load_fe(X, tab, 6 * e + 0);
+    tab_load_fe(Y, tab, 6 * e + 2);
+    tab_load_fe(Z, tab, 6 * e + 4);
+    if ((d < 0) != flip) F::neg(Y, Y);
+    if (C::kGlv && endo) C::mul_beta(X, X);
+    jac_add<C>(acc, X, Y, Z);
+}
+
+// acc += sign(d) * |d| * G from the shared affine table (entry j-1 = j*G: x at words [16(j-1), +8), y next)
+template <class C>
+SG_HD void sw_add_from_gtab(JacPoint& acc, const u32* gtab, int d, bool flip, bool endo) {
+    typedef typename C::F F;
+    if (d == 0) return;
+    int e = (d < 0 ? -d : d) - 1;
+    Fe x, y;
+    const Q4* q = reinterpret_cast<const Q4*>(gtab) + 4 * e;
+    Q4 a = q[0], b = q[1], c = q[2], dd = q[3];
+    x.v[0] = a.x; x.v[1] = a.y; x.v[2] = a.z; x.v[3] = a.w;
+    x.v[4] = b.x; x.v[5] = b.y; x.v[6] = b.z; x.v[7] = b.w;
+    y.v[0] = c.x; y.v[1] = c.y; y.v[2] = c.z; y.v[3] = c.w;
+    y.v[4] = dd.x; y.v[5] = dd.y; y.v[6] = dd.z; y.v[7] = dd.w;
+    if ((d < 0) != flip) F::neg(y, y);
+    if (C::kGlv && endo) C::mul_beta(x, x);
+    jac_madd<C>(acc, x, y);
+}
+
+// Q = u1*G + u2*R.  secp256k1: u1, u2 are GLV-split into four <=128-bit streams, 33 signed 4-bit windows for the
+// R streams and 17 signed 8-bit windows for the G streams share 128 doublings.  secp256r1: two 256-bit streams,
+// 65 / 33 windows over 256 doublings.
+template <class C>
+SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabRef& tab, const u32* gtab) {
+    acc.inf = true;
+    C::F::set_zero(acc.X);
+    C::F::set_zero(acc.Y);
+    C::F::set_zero(acc.Z);
+    if (C::kGlv) {
+        GlvSplit sr, sg;
+        k1_glv_split(sr, u2);
+        k1_glv_split(sg, u1);
+        u32 kp[4][5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            kp[0][i] = sr.k1[i];
+            kp[1][i] = sr.k2[i];
+            kp[2][i] = sg.k1[i];
+            kp[3][i] = sg.k2[i];
+        }
+        recode_add_offset<5>(kp[0], 0x88888888u, 0x8u);
+        recode_add_offset<5>(kp[1], 0x88888888u, 0x8u);
+        recode_add_offset<5>(kp[2], 0x80808080u, 0x80u);
+        recode_add_offset<5>(kp[3], 0x80808080u, 0x80u);
+        const bool flip[4] = {sr.neg1, sr.neg2, sg.neg1, sg.neg2};
+#pragma unroll 1
+        for (int i = 32; i >= 0; i--) {
+            if (i != 32) {
+#pragma unroll 1
+                for (int d = 0; d < 4; d++) jac_dbl<C>(acc);
+            }
+#pragma unroll 1
+            for (int s = 0; s < 2; s++) sw_add_from_table<C>(acc, tab, recode_digit<4>(kp[s], i), flip[s], s == 1);
+            if ((i & 1) == 0) {
+#pragma unroll 1
+                for (int s = 2; s < 4; s++)
+                    sw_add_from_gtab<C>(acc, gtab, recode_digit<8>(kp[s], i >> 1), flip[s], s == 3);
+            }
+        }
+    } else {
+        u32 kp[2][9];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            kp[0][i] = u2[i];
+            kp[1][i] = u1[i];
+        }
+        kp[0][8] = 0;
+        kp[1][8] = 0;
+        recode_add_offset<9>(kp[0], 0x88888888u, 0x8u);
+        recode_add_offset<9>(kp[1], 0x80808080u, 0x80u);
+#pragma unroll 1
+        for (int i = 64; i >= 0; i--) {
+            if (i != 64) {
+#pragma unroll 1
+                for (int d = 0; d < 4; d++) jac_dbl<C>(acc);
+            }
+            sw_add_from_table<C>(acc, tab, recode_digit<4>(kp[0], i), false, false);
+            if ((i & 1) == 0) sw_add_from_gtab<C>(acc, gtab, recode_digit<8>(kp[1], i >> 1), false, false);
+        }
+    }
+}
+
+// One signature.  sig_w / msg_w: the 64 / 32 input bytes as little-endian-loaded 32-bit words.
+// out_w: 16 words (X || Y big-endian bytes, again as little-endian-loaded words); all zero when invalid.
+// Returns the status byte: 0 = recovered, 1 = invalid signature (the CPU libraries' Err(InvalidSignature)).
+template <class C>
+SG_HD u32 sw_ecrecover_one(u32* out_w, const u32* sig_w, const u32* msg_w, const TabRef& tab, const u32* gtab) {
+    typedef typename C::F F;
+    typedef typename C::S S;
+#pragma unroll
+    for (int i = 0; i < 16; i++) out_w[i] = 0;
+    // decode_signature: y parity is bit 7 of byte 32 (src/wgsl/signature.wgsl:6-21, src/tests/mod.rs:151-163)
+    u32 r[8], s[8], z[8];
+    be_words_to_limbs(r, sig_w);
+    u32 sw[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) sw[i] = sig_w[8 + i];
+    u32 parity = (sw[0] >> 7) & 1u;
+    sw[0] &= ~0x80u;
+    be_words_to_limbs(s, sw);
+    be_words_to_limbs(z, msg_w);
+    if (is_zero8(r) || is_zero8(s) || !S::lt_mod(r) || !S::lt_mod(s)) return 1;
+    S::reduce_once(z, z);
+    // lift x = r
+    Fe x, y, t, y2;
+    F::from_plain(x, r);
+    C::rhs(t, x);
+    fe_sqrt_candidate((F*)0, y, t);
+    F::sqr(y2, y);
+    if (!F::eq(y2, t)) return 1;
+    {
+        u32 yp[8];
+        F::to_plain(yp, y);
+        if ((yp[0] & 1u) != parity) F::neg(y, y);
+    }
+    // u1 = -z/r, u2 = s/r  (mod n)
+    u32 rm[8], rinv[8], u1[8], u2[8];
+    S::to_mont(rm, r);
+    S::minv(rinv, rm);
+    S::mmul(u2, rinv, s);
+    S::mmul(u1, rinv, z);
+    S::neg(u1, u1);
+    // Q = u1*G + u2*R
+    sw_build_table<C>(tab, x, y);
+    JacPoint Q;
+    sw_double_mul<C>(Q, u1, u2, tab, gtab);
+    if (Q.inf) return 1;
+    Fe zi, zi2, ax, ay;
+    fe_inv((F*)0, zi, Q.Z);
+    F::sqr(zi2, zi);
+    F::mul(ax, Q.X, zi2);
+    F::mul(zi2, zi2, zi);
+    F::mul(ay, Q.Y, zi2);
+    u32 xp[8], yp[8];
+    F::to_plain(xp, ax);
+    F::to_plain(yp, ay);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        out_w[i] = bswap32(xp[7 - i]);
+        out_w[8 + i] = bswap32(yp[7 - i]);
+    }
+    return 0;
+}
+
+}  // namespace sigops

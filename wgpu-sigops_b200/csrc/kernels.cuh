@@ -1,0 +1,427 @@
+// __global__ entry points: one fused kernel per curve (replaces the 5 / 6 / 7 dispatches of
+// src/secp256k1_ecdsa.rs:61-213, src/secp256r1_ecdsa.rs:62-214 and src/ed25519_eddsa.rs:67-257 and the
+// intermediate storage buffers between them), the unit-test shims (the role of src/wgsl/tests/*.wgsl) and
+// the integer-pipe micro-benchmark.
+//
+// Launch geometry: 1-D grid, 128 threads per block, a bounded number of blocks (a multiple of the SM count)
+// and a grid-stride loop over signatures -- no power-of-two padding, no 3-D workgroup lookup table
+// (src/benchmarks/mod.rs:10-53 `compute_num_workgroups`, src/secp256k1_ecdsa.rs:24-47).
+#pragma once
+#include "../../include/sigops.h"
+#include "curve_ed.cuh"
+
+namespace sigops {
+
+static constexpr int kBlock = 128;
+
+#if defined(__CUDACC__)
+
+// Copy a constant table into shared memory (generator table staged per block)
+__device__ __forceinline__ void stage_table(u32* dst, const u32* src, int words) {
+    const Q4* s = reinterpret_cast<const Q4*>(src);
+    Q4* d = reinterpret_cast<Q4*>(dst);
+    for (int i = threadIdx.x; i < words / 4; i += blockDim.x) d[i] = s[i];
+    __syncthreads();
+}
+
+template <class C>
+__global__ void __launch_bounds__(kBlock) ecrecover_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
+                                                           size_t n, Q4* __restrict__ out, uint8_t* __restrict__ status,
+                                                           Q4* __restrict__ scratch, const u32* __restrict__ gtab_g) {
+    __shared__ __align__(16) u32 gtab[SG_GTAB_ENTRIES * 16];
+    stage_table(gtab, gtab_g, SG_GTAB_ENTRIES * 16);
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TabRef tab;
+    tab.base = scratch + gid;
+    tab.stride = (u32)nthreads;
+    for (size_t i = gid; i < n; i += nthreads) {
+        u32 sig_w[16], msg_w[8], out_w[16];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            Q4 v = sigs[4 * i + q];
+            sig_w[4 * q + 0] = v.x;
+            sig_w[4 * q + 1] = v.y;
+            sig_w[4 * q + 2] = v.z;
+            sig_w[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            Q4 v = msgs[2 * i + q];
+            msg_w[4 * q + 0] = v.x;
+            msg_w[4 * q + 1] = v.y;
+            msg_w[4 * q + 2] = v.z;
+            msg_w[4 * q + 3] = v.w;
+        }
+        u32 st = sw_ecrecover_one<C>(out_w, sig_w, msg_w, tab, gtab);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            Q4 v = {out_w[4 * q + 0], out_w[4 * q + 1], out_w[4 * q + 2], out_w[4 * q + 3]};
+            out[4 * i + q] = v;
+        }
+        if (status) status[i] = (uint8_t)st;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) ed25519_verify_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
+                                                                const Q4* __restrict__ pks, size_t n,
+                                                                uint8_t* __restrict__ valid, Q4* __restrict__ scratch,
+                                                                const u32* __restrict__ btab_g) {
+    __shared__ __align__(16) u32 btab[SG_GTAB_ENTRIES * 24];
+    stage_table(btab, btab_g, SG_GTAB_ENTRIES * 24);
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TabRef tab;
+    tab.base = scratch + gid;
+    tab.stride = (u32)nthreads;
+    for (size_t i = gid; i < n; i += nthreads) {
+        u32 sig_w[16], msg_w[8], pk_w[8];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            Q4 v = sigs[4 * i + q];
+            sig_w[4 * q + 0] = v.x;
+            sig_w[4 * q + 1] = v.y;
+            sig_w[4 * q + 2] = v.z;
+            sig_w[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            Q4 v = msgs[2 * i + q];
+            msg_w[4 * q + 0] = v.x;
+            msg_w[4 * q + 1] = v.y;
+            msg_w[4 * q + 2] = v.z;
+            msg_w[4 * q + 3] = v.w;
+            Q4 p = pks[2 * i + q];
+            pk_w[4 * q + 0] = p.x;
+            pk_w[4 * q + 1] = p.y;
+            pk_w[4 * q + 2] = p.z;
+            pk_w[4 * q + 3] = p.w;
+        }
+        valid[i] = (uint8_t)ed_verify_one(sig_w, msg_w, pk_w, tab, btab);
+    }
+}
+
+#endif  // __CUDACC__
+
+// ---------------------------------------------------------------------------------------------------------
+// unit-test shims: one item per thread, words in / words out
+// ---------------------------------------------------------------------------------------------------------
+SG_HD void unit_shape(int op, int& in_w, int& out_w) {
+    in_w = 8;
+    out_w = 8;
+    switch (op) {
+        case SIGOPS_UNIT_K1_MUL: case SIGOPS_UNIT_K1_ADD: case SIGOPS_UNIT_K1_SUB:
+        case SIGOPS_UNIT_R1_MUL: case SIGOPS_UNIT_R1_ADD: case SIGOPS_UNIT_R1_SUB:
+        case SIGOPS_UNIT_ED_MUL: case SIGOPS_UNIT_ED_ADD: case SIGOPS_UNIT_ED_SUB:
+        case SIGOPS_UNIT_K1N_MUL: case SIGOPS_UNIT_R1N_MUL:
+            in_w = 16;
+            break;
+        case SIGOPS_UNIT_EDL_REDUCE512:
+            in_w = 16;
+            break;
+        case SIGOPS_UNIT_SHA512_96:
+            in_w = 24;
+            out_w = 16;
+            break;
+        case SIGOPS_UNIT_K1_GLV:
+            out_w = 12;
+            break;
+        case SIGOPS_UNIT_MUL8X8:
+            in_w = 16;
+            out_w = 16;
+            break;
+        case SIGOPS_UNIT_SQR8:
+            out_w = 16;
+            break;
+        case SIGOPS_UNIT_K1_MULPT: case SIGOPS_UNIT_R1_MULPT:
+            in_w = 24;
+            out_w = 17;
+            break;
+        case SIGOPS_UNIT_ED_MULPT:
+            in_w = 24;
+            out_w = 16;
+            break;
+        case SIGOPS_UNIT_K1_DOUBLE_MUL: case SIGOPS_UNIT_R1_DOUBLE_MUL:
+            in_w = 32;
+            out_w = 17;
+            break;
+        default:
+            break;
+    }
+}
+
+template <class F>
+SG_HD void unit_field(int which, u32* out, const u32* in) {
+    // which: 0 mul, 1 sqr, 2 add, 3 sub, 4 inv, 5 sqrt-candidate
+    Fe a, b, r;
+    F::from_plain(a, in);
+    if (which == 0 || which == 2 || which == 3) F::from_plain(b, in + 8);
+    switch (which) {
+        case 0: F::mul(r, a, b); break;
+        case 1: F::sqr(r, a); break;
+        case 2: F::add(r, a, b); break;
+        case 3: F::sub(r, a, b); break;
+        default: break;
+    }
+    F::to_plain(out, r);
+}
+
+template <class C>
+SG_HD void unit_double_mul(u32* out, const u32* u1, const u32* u2, const u32* xy, const TabRef& tab, const u32* gtab) {
+    typedef typename C::F F;
+    Fe x, y;
+    F::from_plain(x, xy);
+    F::from_plain(y, xy + 8);
+    sw_build_table<C>(tab, x, y);
+    JacPoint Q;
+    sw_double_mul<C>(Q, u1, u2, tab, gtab);
+    for (int i = 0; i < 17; i++) out[i] = 0;
+    if (Q.inf) {
+        out[16] = 1;
+        return;
+    }
+    Fe zi, zi2, ax, ay;
+    fe_inv((F*)0, zi, Q.Z);
+    F::sqr(zi2, zi);
+    F::mul(ax, Q.X, zi2);
+    F::mul(zi2, zi2, zi);
+    F::mul(ay, Q.Y, zi2);
+    F::to_plain(out, ax);
+    F::to_plain(out + 8, ay);
+}
+
+// dispatcher shared by the device shim kernel and the host simulation
+SG_HD void unit_dispatch(int op, u32* out, const u32* in, const TabRef& tab, const u32* k1g, const u32* r1g,
+                         const u32* edb) {
+    switch (op) {
+        case SIGOPS_UNIT_K1_MUL: case SIGOPS_UNIT_K1_SQR: case SIGOPS_UNIT_K1_ADD: case SIGOPS_UNIT_K1_SUB:
+            unit_field<FpK1>(op - SIGOPS_UNIT_K1_MUL, out, in);
+            break;
+        case SIGOPS_UNIT_R1_MUL: case SIGOPS_UNIT_R1_SQR: case SIGOPS_UNIT_R1_ADD: case SIGOPS_UNIT_R1_SUB:
+            unit_field<FpR1>(op - SIGOPS_UNIT_R1_MUL, out, in);
+            break;
+        case SIGOPS_UNIT_ED_MUL: case SIGOPS_UNIT_ED_SQR: case SIGOPS_UNIT_ED_ADD: case SIGOPS_UNIT_ED_SUB:
+            unit_field<Fp25519>(op - SIGOPS_UNIT_ED_MUL, out, in);
+            break;
+        case SIGOPS_UNIT_K1_INV: case SIGOPS_UNIT_K1_SQRT: {
+            Fe a, r;
+            FpK1::from_plain(a, in);
+            if (op == SIGOPS_UNIT_K1_INV) fe_inv((FpK1*)0, r, a); else fe_sqrt_candidate((FpK1*)0, r, a);
+            FpK1::to_plain(out, r);
+            break;
+        }
+        case SIGOPS_UNIT_R1_INV: case SIGOPS_UNIT_R1_SQRT: {
+            Fe a, r;
+            FpR1::from_plain(a, in);
+            if (op == SIGOPS_UNIT_R1_INV) fe_inv((FpR1*)0, r, a); else fe_sqrt_candidate((FpR1*)0, r, a);
+            FpR1::to_plain(out, r);
+            break;
+        }
+        case SIGOPS_UNIT_ED_INV: case SIGOPS_UNIT_ED_POW_P58: {
+            Fe a, r;
+            Fp25519::from_plain(a, in);
+            if (op == SIGOPS_UNIT_ED_INV) fe_inv((Fp25519*)0, r, a); else fe_pow_p58(r, a);
+            Fp25519::to_plain(out, r);
+            break;
+        }
+        case SIGOPS_UNIT_K1N_MUL: {
+            u32 am[8];
+            Sc<ModK1N>::to_mont(am, in);
+            Sc<ModK1N>::mmul(out, am, in + 8);
+            break;
+        }
+        case SIGOPS_UNIT_R1N_MUL: {
+            u32 am[8];
+            Sc<ModR1N>::to_mont(am, in);
+            Sc<ModR1N>::mmul(out, am, in + 8);
+            break;
+        }
+        case SIGOPS_UNIT_K1N_INV: {
+            u32 am[8], im[8];
+            Sc<ModK1N>::to_mont(am, in);
+            Sc<ModK1N>::minv(im, am);
+            Sc<ModK1N>::from_mont(out, im);
+            break;
+        }
+        case SIGOPS_UNIT_R1N_INV: {
+            u32 am[8], im[8];
+            Sc<ModR1N>::to_mont(am, in);
+            Sc<ModR1N>::minv(im, am);
+            Sc<ModR1N>::from_mont(out, im);
+            break;
+        }
+        case SIGOPS_UNIT_EDL_REDUCE512:
+            ed_reduce512(out, in);
+            break;
+        case SIGOPS_UNIT_SHA512_96:
+            sha512_96(out, in);
+            break;
+        case SIGOPS_UNIT_K1_GLV: {
+            GlvSplit s;
+            k1_glv_split(s, in);
+            for (int i = 0; i < 5; i++) {
+                out[i] = s.k1[i];
+                out[5 + i] = s.k2[i];
+            }
+            out[10] = s.neg1;
+            out[11] = s.neg2;
+            break;
+        }
+        case SIGOPS_UNIT_MUL8X8:
+            mul8x8(out, in, in + 8);
+            break;
+        case SIGOPS_UNIT_SQR8:
+            sqr8(out, in);
+            break;
+        case SIGOPS_UNIT_K1_MULPT: {
+            const u32 zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            unit_double_mul<CurveK1>(out, zero, in, in + 8, tab, k1g);
+            break;
+        }
+        case SIGOPS_UNIT_R1_MULPT: {
+            const u32 zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            unit_double_mul<CurveR1>(out, zero, in, in + 8, tab, r1g);
+            break;
+        }
+        case SIGOPS_UNIT_K1_DOUBLE_MUL:
+            unit_double_mul<CurveK1>(out, in, in + 8, in + 16, tab, k1g);
+            break;
+        case SIGOPS_UNIT_R1_DOUBLE_MUL:
+            unit_double_mul<CurveR1>(out, in, in + 8, in + 16, tab, r1g);
+            break;
+        case SIGOPS_UNIT_ED_MULPT: {
+            // k*(x,y) by the same windowed ladder the verifier uses (table of multiples, signed 4-bit windows)
+            Fe x, y;
+            Fp25519::from_plain(x, in + 8);
+            Fp25519::from_plain(y, in + 16);
+            EdPoint P1, P2, P3, P4, T, acc;
+            P1.X = x;
+            P1.Y = y;
+            FE::set_one(P1.Z);
+            FE::mul(P1.T, x, y);
+            ed_tab_store(tab, 0, P1);
+            Fe ypx, ymx, t2d;
+            const Fe d2 = {SG_ED_D2};
+            FE::add(ypx, y, x);
+            FE::sub(ymx, y, x);
+            FE::mul(t2d, P1.T, d2);
+            P2 = P1; ed_dbl(P2, true); ed_tab_store(tab, 1, P2);
+            P3 = P2; ed_add_niels(P3, ypx, ymx, t2d, false, true); ed_tab_store(tab, 2, P3);
+            P4 = P2; ed_dbl(P4, true); ed_tab_store(tab, 3, P4);
+            T = P4; ed_add_niels(T, ypx, ymx, t2d, false, true); ed_tab_store(tab, 4, T);
+            T = P3; ed_dbl(T, true); ed_tab_store(tab, 5, T);
+            ed_add_niels(T, ypx, ymx, t2d, false, true); ed_tab_store(tab, 6, T);
+            T = P4; ed_dbl(T, true); ed_tab_store(tab, 7, T);
+            u32 kp[9];
+            for (int i = 0; i < 8; i++) kp[i] = in[i];
+            kp[8] = 0;
+            recode_add_offset<9>(kp, 0x88888888u, 0x8u);
+            ed_set_identity(acc);
+            for (int i = 64; i >= 0; i--) {
+                if (i != 64) {
+                    ed_dbl(acc, false); ed_dbl(acc, false); ed_dbl(acc, false); ed_dbl(acc, true);
+                }
+                ed_add_from_table(acc, tab, recode_digit<4>(kp, i), true);
+            }
+            Fe zi, ax, ay;
+            fe_inv((FE*)0, zi, acc.Z);
+            FE::mul(ax, acc.X, zi);
+            FE::mul(ay, acc.Y, zi);
+            FE::to_plain(out, ax);
+            FE::to_plain(out + 8, ay);
+            (void)edb;
+            break;
+        }
+        default:
+            break;
+    }
+}
+
+#if defined(__CUDACC__)
+__global__ void __launch_bounds__(kBlock) unit_kernel(int op, const u32* __restrict__ in, size_t n, u32* __restrict__ out,
+                                                      Q4* __restrict__ scratch, const u32* k1g, const u32* r1g,
+                                                      const u32* edb) {
+    int in_w, out_w;
+    unit_shape(op, in_w, out_w);
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TabRef tab;
+    tab.base = scratch + gid;
+    tab.stride = (u32)nthreads;
+    for (size_t i = gid; i < n; i += nthreads) {
+        u32 a[32], r[17];
+        for (int j = 0; j < 32; j++) a[j] = j < in_w ? in[i * in_w + j] : 0u;
+        for (int j = 0; j < 17; j++) r[j] = 0;
+        unit_dispatch(op, r, a, tab, k1g, r1g, edb);
+        for (int j = 0; j < out_w; j++) out[i * out_w + j] = r[j];
+    }
+}
+
+// ---- integer-pipe micro-benchmark: 8 independent accumulator chains per thread, fully unrolled inner block ----
+template <int KIND>
+__global__ void __launch_bounds__(256) imad_peak_kernel(u32* sink, int iters, u32 seed) {
+    u32 a0 = seed + threadIdx.x, a1 = a0 * 3 + 1, a2 = a0 * 5 + 2, a3 = a0 * 7 + 3;
+    u32 a4 = a0 * 9 + 4, a5 = a0 * 11 + 5, a6 = a0 * 13 + 6, a7 = a0 * 15 + 7;
+    u32 b0 = a7, b1 = a6, b2 = a5, b3 = a4, b4 = a3, b5 = a2, b6 = a1, b7 = a0;
+    u32 x = seed | 1u, y = (seed >> 3) | 5u;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            if (KIND == 0) {
+                asm volatile(
+                    "mad.lo.u32 %0, %0, %8, %9;\n\tmad.lo.u32 %1, %1, %8, %9;\n\tmad.lo.u32 %2, %2, %8, %9;\n\t"
+                    "mad.lo.u32 %3, %3, %8, %9;\n\tmad.lo.u32 %4, %4, %8, %9;\n\tmad.lo.u32 %5, %5, %8, %9;\n\t"
+                    "mad.lo.u32 %6, %6, %8, %9;\n\tmad.lo.u32 %7, %7, %8, %9;"
+                    : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7)
+                    : "r"(x), "r"(y));
+            } else if (KIND == 1) {
+                // 8 independent 64-bit accumulators (aK,bK) += x*y : IMAD.WIDE.U32 without carry chain
+                asm volatile(
+                    "{.reg .u64 t0,t1,t2,t3,t4,t5,t6,t7;\n\t"
+                    "mov.b64 t0,{%0,%8}; mov.b64 t1,{%1,%9}; mov.b64 t2,{%2,%10}; mov.b64 t3,{%3,%11};\n\t"
+                    "mov.b64 t4,{%4,%12}; mov.b64 t5,{%5,%13}; mov.b64 t6,{%6,%14}; mov.b64 t7,{%7,%15};\n\t"
+                    "mad.wide.u32 t0,%0,%16,t0; mad.wide.u32 t1,%1,%16,t1; mad.wide.u32 t2,%2,%16,t2; mad.wide.u32 t3,%3,%16,t3;\n\t"
+                    "mad.wide.u32 t4,%4,%16,t4; mad.wide.u32 t5,%5,%16,t5; mad.wide.u32 t6,%6,%16,t6; mad.wide.u32 t7,%7,%16,t7;\n\t"
+                    "mov.b64 {%0,%8},t0; mov.b64 {%1,%9},t1; mov.b64 {%2,%10},t2; mov.b64 {%3,%11},t3;\n\t"
+                    "mov.b64 {%4,%12},t4; mov.b64 {%5,%13},t5; mov.b64 {%6,%14},t6; mov.b64 {%7,%15},t7;}"
+                    : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7), "+r"(b0),
+                      "+r"(b1), "+r"(b2), "+r"(b3), "+r"(b4), "+r"(b5), "+r"(b6), "+r"(b7)
+                    : "r"(x));
+            } else if (KIND == 2) {
+                // two 4-product carry chains (the shape of one row of the field multiplication)
+                asm volatile(
+                    "mad.lo.cc.u32 %0,%16,%17,%0; madc.hi.cc.u32 %1,%16,%17,%1; madc.lo.cc.u32 %2,%17,%16,%2; madc.hi.cc.u32 %3,%17,%16,%3;\n\t"
+                    "madc.lo.cc.u32 %4,%16,%16,%4; madc.hi.cc.u32 %5,%16,%16,%5; madc.lo.cc.u32 %6,%17,%17,%6; madc.hi.u32 %7,%17,%17,%7;\n\t"
+                    "mad.lo.cc.u32 %8,%16,%17,%8; madc.hi.cc.u32 %9,%16,%17,%9; madc.lo.cc.u32 %10,%17,%16,%10; madc.hi.cc.u32 %11,%17,%16,%11;\n\t"
+                    "madc.lo.cc.u32 %12,%16,%16,%12; madc.hi.cc.u32 %13,%16,%16,%13; madc.lo.cc.u32 %14,%17,%17,%14; madc.hi.u32 %15,%17,%17,%15;"
+                    : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7), "+r"(b0),
+                      "+r"(b1), "+r"(b2), "+r"(b3), "+r"(b4), "+r"(b5), "+r"(b6), "+r"(b7)
+                    : "r"(x), "r"(y));
+            } else if (KIND == 3) {
+                asm volatile(
+                    "add.u32 %0, %0, %8;\n\tadd.u32 %1, %1, %9;\n\tadd.u32 %2, %2, %8;\n\tadd.u32 %3, %3, %9;\n\t"
+                    "add.u32 %4, %4, %8;\n\tadd.u32 %5, %5, %9;\n\tadd.u32 %6, %6, %8;\n\tadd.u32 %7, %7, %9;"
+                    : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7)
+                    : "r"(x), "r"(y));
+            } else {
+                asm volatile(
+                    "{.reg .u64 t0,t1,t2,t3;\n\t"
+                    "mov.b64 t0,{%0,%4}; mov.b64 t1,{%1,%5}; mov.b64 t2,{%2,%6}; mov.b64 t3,{%3,%7};\n\t"
+                    "mad.wide.u32 t0,%0,%16,t0; add.u32 %8,%8,%17; mad.wide.u32 t1,%1,%16,t1; add.u32 %9,%9,%17;\n\t"
+                    "mad.wide.u32 t2,%2,%16,t2; add.u32 %10,%10,%17; mad.wide.u32 t3,%3,%16,t3; add.u32 %11,%11,%17;\n\t"
+                    "mad.wide.u32 t0,%1,%16,t0; add.u32 %12,%12,%17; mad.wide.u32 t1,%2,%16,t1; add.u32 %13,%13,%17;\n\t"
+                    "mad.wide.u32 t2,%3,%16,t2; add.u32 %14,%14,%17; mad.wide.u32 t3,%0,%16,t3; add.u32 %15,%15,%17;\n\t"
+                    "mov.b64 {%0,%4},t0; mov.b64 {%1,%5},t1; mov.b64 {%2,%6},t2; mov.b64 {%3,%7},t3;}"
+                    : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7), "+r"(b0),
+                      "+r"(b1), "+r"(b2), "+r"(b3), "+r"(b4), "+r"(b5), "+r"(b6), "+r"(b7)
+                    : "r"(x), "r"(y));
+            }
+        }
+    }
+    u32 r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7 ^ b0 ^ b1 ^ b2 ^ b3 ^ b4 ^ b5 ^ b6 ^ b7;
+    if (r == 0x12345678u) sink[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+#endif  // __CUDACC__
+
+}  // namespace sigops

@@ -1,0 +1,239 @@
+// Scalar-field arithmetic (mod the group orders n_k1, n_r1 and the ed25519 order L), the secp256k1 GLV
+// split and the fixed signed-window recoding used by the interleaved double-scalar multiplication.
+//
+// Replaces: src/wgsl/ff.wgsl:60-120 `ff_inverse` (binary extended GCD, variable time / divergent) and the
+// Barrett `ff_mul` mod n (src/wgsl/ff.wgsl:169-198) used by src/wgsl/secp256k1_ecdsa.wgsl:56-80;
+// src/wgsl/ed25519_reduce_fr.wgsl:88-125 (512-bit hash -> mod L); src/wgsl/bigint.wgsl `bigint_to_bits_le`
+// (bit decomposition by 256 full-width halvings) -- here scalar digits are read with shifts.
+// The GLV lattice constants are the ones the reference carries at src/curve_algos/secp256k1_curve.rs:47-68
+// (its split procedure, src/curve_algos/secp256k1_mul.rs:51-85, is test-only there; the WGSL never uses it).
+#pragma once
+#include "field.cuh"
+#include "consts_gen.cuh"
+
+namespace sigops {
+
+// ---------------------------------------------------------------------------------------------------------
+// generic Montgomery arithmetic mod an odd 256-bit modulus, R = 2^256
+// ---------------------------------------------------------------------------------------------------------
+struct ModK1N {
+    static SG_HD void mod(u32* m) {
+        const u32 M[8] = SG_K1_N;
+        copy8(m, M);
+    }
+    static SG_HD void r2(u32* m) {
+        const u32 M[8] = SG_K1_N_R2;
+        copy8(m, M);
+    }
+    static SG_HD void minus2(u32* m) {
+        const u32 M[8] = SG_K1_N_MINUS2;
+        copy8(m, M);
+    }
+    static constexpr u32 n0inv = SG_K1_N_N0INV;
+};
+struct ModR1N {
+    static SG_HD void mod(u32* m) {
+        const u32 M[8] = SG_R1_N;
+        copy8(m, M);
+    }
+    static SG_HD void r2(u32* m) {
+        const u32 M[8] = SG_R1_N_R2;
+        copy8(m, M);
+    }
+    static SG_HD void minus2(u32* m) {
+        const u32 M[8] = SG_R1_N_MINUS2;
+        copy8(m, M);
+    }
+    static constexpr u32 n0inv = SG_R1_N_N0INV;
+};
+struct ModEdL {
+    static SG_HD void mod(u32* m) {
+        const u32 M[8] = SG_ED_L;
+        copy8(m, M);
+    }
+    static SG_HD void r2(u32* m) {
+        const u32 M[8] = SG_ED_L_R2;
+        copy8(m, M);
+    }
+    static SG_HD void minus2(u32* m) {
+        const u32 M[8] = SG_ED_L_MINUS2;
+        copy8(m, M);
+    }
+    static constexpr u32 n0inv = SG_ED_L_N0INV;
+};
+
+template <class M>
+struct Sc {
+    // r = t / 2^256 mod m, for t < 2^256 * m.  Lazy carries: the carry out of each row lands above every limb
+    // that still determines a quotient digit, so they are summed once at the end.
+    static SG_HD void reduce16(u32* r, const u32* tin) {
+        u32 m[8];
+        M::mod(m);
+        u32 t[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) t[i] = tin[i];
+        u32 cr[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) cr[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            u32 q = t[i] * M::n0inv;
+            cr[i] += mad_row4(t + i, m[0], m[2], m[4], m[6], q);
+            cr[i + 1] += mad_row4(t + i + 1, m[1], m[3], m[5], m[7], q);
+        }
+        u32 s[8];
+        u32 c = add8(s, t + 8, cr);
+        u32 top = cr[8] + c;
+        u32 u[8];
+        u32 bw = sub8(u, s, m);
+        select8(r, (top != 0) || (bw == 0), s, u);
+    }
+    // Montgomery product a*b/R mod m; requires a < 2^256, b < m (or a*b < 2^256*m)
+    static SG_HD void mmul(u32* r, const u32* a, const u32* b) {
+        u32 t[16];
+        mul8x8(t, a, b);
+        reduce16(r, t);
+    }
+    static SG_HD void msqr(u32* r, const u32* a) {
+        u32 t[16];
+        sqr8(t, a);
+        reduce16(r, t);
+    }
+    static SG_HD void to_mont(u32* r, const u32* a) {
+        u32 r2[8];
+        M::r2(r2);
+        mmul(r, a, r2);
+    }
+    static SG_HD void from_mont(u32* r, const u32* a) {
+        u32 t[16];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            t[i] = a[i];
+            t[i + 8] = 0;
+        }
+        reduce16(r, t);
+    }
+    // r = a mod m for a < 2m
+    static SG_HD void reduce_once(u32* r, const u32* a) {
+        u32 m[8], u[8];
+        M::mod(m);
+        u32 bw = sub8(u, a, m);
+        select8(r, bw == 0, a, u);
+    }
+    static SG_HD void neg(u32* r, const u32* a) {  // a in [0,m)
+        u32 m[8], u[8];
+        M::mod(m);
+        sub8(u, m, a);
+        select8(r, is_zero8(a), u, a);
+    }
+    static SG_HD bool lt_mod(const u32* a) {
+        u32 m[8];
+        M::mod(m);
+        return !gte8(a, m);
+    }
+    // Montgomery-domain inverse by Fermat: a^(m-2), fixed 4-bit windows (256 squarings + 64 + 14 products)
+    static SG_HD void minv(u32* r, const u32* a) {
+        u32 e[8];
+        M::minus2(e);
+        u32 tab[15][8];  // a^1..a^15
+        copy8(tab[0], a);
+#pragma unroll 1
+        for (int i = 1; i < 15; i++) mmul(tab[i], tab[i - 1], a);
+        u32 acc[8];
+        {
+            u32 d = e[7] >> 28;  // top nibble is nonzero for all three moduli
+            copy8(acc, tab[d - 1]);
+        }
+#pragma unroll 1
+        for (int w = 62; w >= 0; w--) {
+            msqr(acc, acc);
+            msqr(acc, acc);
+            msqr(acc, acc);
+            msqr(acc, acc);
+            u32 d = (e[w >> 3] >> ((w & 7) * 4)) & 15u;
+            if (d) mmul(acc, acc, tab[d - 1]);
+        }
+        copy8(r, acc);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// secp256k1 GLV split: k = k1 + k2*lambda (mod n), |k1|,|k2| < 2^128.  Plain integer arithmetic mod 2^256:
+//   c1 = round(k*g1 / 2^384), c2 = round(k*g2 / 2^384)
+//   k1 = k - c1*a1 - c2*a2,   k2 = c1*(-b1) - c2*b2        (b2 = a1)
+// ---------------------------------------------------------------------------------------------------------
+struct GlvSplit {
+    u32 k1[5], k2[5];  // magnitudes (fit in 128 bits; limb 4 is zero, kept for the recoding offset)
+    bool neg1, neg2;
+};
+
+SG_HD void neg256(u32* r, const u32* a) {
+    u32 z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    sub8(r, z, a);
+}
+
+SG_HD void k1_glv_split(GlvSplit& out, const u32* k) {
+    const u32 G1[8] = SG_K1_G1, G2[8] = SG_K1_G2, A1[8] = SG_K1_A1, A2[8] = SG_K1_A2, MB1[8] = SG_K1_MB1;
+    u32 t[16], c1[8], c2[8];
+    const u32 half[8] = {0, 0, 0, 0x80000000u, 0, 0, 0, 0};  // 2^383 relative to limb 8
+    mul8x8(t, k, G1);
+    add8(t + 8, t + 8, half);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        c1[i] = t[12 + i];
+        c1[4 + i] = 0;
+    }
+    mul8x8(t, k, G2);
+    add8(t + 8, t + 8, half);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        c2[i] = t[12 + i];
+        c2[4 + i] = 0;
+    }
+    u32 p1[16], p2[16], r1[8], r2[8];
+    mul8x8(p1, c1, A1);
+    mul8x8(p2, c2, A2);
+    sub8(r1, k, p1);
+    sub8(r1, r1, p2);
+    mul8x8(p1, c1, MB1);
+    mul8x8(p2, c2, A1);
+    sub8(r2, p1, p2);
+    out.neg1 = (r1[7] >> 31) != 0;
+    out.neg2 = (r2[7] >> 31) != 0;
+    if (out.neg1) neg256(r1, r1);
+    if (out.neg2) neg256(r2, r2);
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        out.k1[i] = r1[i];
+        out.k2[i] = r2[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fixed signed-window recoding.  For window width W and NW windows, adding the constant
+// C = sum_i 2^(W-1) * 2^(W*i) turns the unsigned windows u_i of k' = k + C into signed digits
+// d_i = u_i - 2^(W-1) in [-2^(W-1), 2^(W-1)) with k = sum d_i 2^(W*i)   (requires k + C < 2^(W*NW)).
+// Every lane adds at the same iterations -> no divergence except on d_i == 0.
+// ---------------------------------------------------------------------------------------------------------
+template <int NLIMBS>
+SG_HD void recode_add_offset(u32* k, u32 pattern, u32 top_pattern) {
+    // k += pattern in limbs 0..NLIMBS-2 and top_pattern in the last limb
+    // (W=4: 0x88888888 / 0x8 or 0x88888888;  W=8: 0x80808080 / 0x80 or 0x80808080)
+    u64 c = 0;
+#pragma unroll
+    for (int i = 0; i < NLIMBS; i++) {
+        c += (u64)k[i] + (i == NLIMBS - 1 ? top_pattern : pattern);
+        k[i] = (u32)c;
+        c >>= 32;
+    }
+}
+
+// signed digit of window i (width W) of the offset scalar k'
+template <int W>
+SG_HD int recode_digit(const u32* kp, int i) {
+    const int per = 32 / W;
+    u32 u = (kp[i / per] >> ((i % per) * W)) & ((1u << W) - 1u);
+    return (int)u - (1 << (W - 1));
+}
+
+}  // namespace sigops
