@@ -1,0 +1,188 @@
+"""Differential checks of the device functions against Python integers / the oracle.
+
+The same checks run against (a) the host simulation of the CUDA headers (CPU, `-m "not gpu"`) and (b) the real
+kernels through `sigops_test_unit` (`-m gpu`).  They mirror the reference's unit tests: bigint/ff
+(src/tests/bigint_and_ff.rs), Montgomery product and square root over several moduli (src/tests/mont.rs), SHA-512 of
+96-byte inputs (src/tests/sha512.rs:12-66), mod-L reduction (src/tests/ed25519_reduce_fr.rs), and the curve tests
+(src/tests/secp256k1_curve.rs, secp256r1_curve.rs, ed25519_curve.rs: scalar multiplication, fixed-base
+multiplication, Strauss-Shamir, to-affine).
+"""
+import hashlib
+import random
+
+import numpy as np
+
+import sigops_oracle as o
+from simlib import edge_values, from_words, rand256
+
+
+def check_field(U, prefix, p, weak, nrand=1500, seed=1):
+    rng = random.Random(seed)
+    ev = edge_values(p) if weak else [v for v in edge_values(p) if v < p]
+    gen = (lambda: rand256(rng)) if weak else (lambda: rand256(rng) % p)
+    pairs = [(a, b) for a in ev for b in ev] + [(gen(), gen()) for _ in range(nrand)]
+    for name, f in (("MUL", lambda a, b: a * b % p), ("ADD", lambda a, b: (a + b) % p), ("SUB", lambda a, b: (a - b) % p)):
+        out = U.run(prefix + "_" + name, pairs)
+        for (a, b), w in zip(pairs, out):
+            assert from_words(w) == f(a, b), (prefix, name, hex(a), hex(b))
+    singles = [(a,) for a, _ in pairs]
+    out = U.run(prefix + "_SQR", singles)
+    for (a,), w in zip(singles, out):
+        assert from_words(w) == a * a % p, (prefix, "SQR", hex(a))
+
+
+def check_wide(U, nrand=1500, seed=2):
+    rng = random.Random(seed)
+    pairs = [(rand256(rng), rand256(rng)) for _ in range(nrand)] + [(2**256 - 1, 2**256 - 1), (0, 0), (2**256 - 1, 1)]
+    out = U.run("MUL8X8", pairs)
+    for (a, b), w in zip(pairs, out):
+        assert from_words(w) == a * b
+    out = U.run("SQR8", [(a,) for a, _ in pairs])
+    for (a, _), w in zip(pairs, out):
+        assert from_words(w) == a * a
+
+
+def check_chains(U, n=40, seed=3):
+    """addition chains: inverse, square root ((p+1)/4 as in src/tests/mont.rs:138-175), (p-5)/8"""
+    rng = random.Random(seed)
+    for prefix, p in (("K1", o.K1.p), ("R1", o.R1.p)):
+        xs = [(rand256(rng) % p,) for _ in range(n)] + [(1,), (2,), (p - 1,)]
+        for (a,), w in zip(xs, U.run(prefix + "_INV", xs)):
+            assert from_words(w) == pow(a, p - 2, p)
+        for (a,), w in zip(xs, U.run(prefix + "_SQRT", xs)):
+            assert from_words(w) == pow(a, (p + 1) // 4, p)
+    p = o.ED_P
+    xs = [(rand256(rng) % p,) for _ in range(n)] + [(1,), (2,), (p - 1,), (0,)]
+    for (a,), w in zip(xs, U.run("ED_INV", xs)):
+        assert from_words(w) == pow(a, p - 2, p)
+    for (a,), w in zip(xs, U.run("ED_POW_P58", xs)):
+        assert from_words(w) == pow(a, (p - 5) // 8, p)
+
+
+def check_scalar(U, n=300, ninv=20, seed=4):
+    rng = random.Random(seed)
+    for prefix, m in (("K1N", o.K1.n), ("R1N", o.R1.n)):
+        pairs = [(rand256(rng) % m, rand256(rng) % m) for _ in range(n)] + [(m - 1, m - 1), (0, 5), (1, 1)]
+        for (a, b), w in zip(pairs, U.run(prefix + "_MUL", pairs)):
+            assert from_words(w) == a * b % m
+        xs = [(rand256(rng) % m,) for _ in range(ninv)] + [(1,), (m - 1,)]
+        for (a,), w in zip(xs, U.run(prefix + "_INV", xs)):
+            assert from_words(w) == pow(a, m - 2, m), (prefix, hex(a))
+    xs = [(rng.getrandbits(512),) for _ in range(n)] + [(2**512 - 1,), (0,), (o.ED_L,), (o.ED_L << 256,), (o.ED_L - 1,)]
+    for (a,), w in zip(xs, U.run("EDL_REDUCE512", xs, widths=[16])):
+        assert from_words(w) == a % o.ED_L
+
+
+def check_sha512(U, n=50, seed=5):
+    rng = random.Random(seed)
+    msgs = [bytes(rng.getrandbits(8) for _ in range(96)) for _ in range(n)] + [bytes(96), b"\xff" * 96]
+    out = U.run_words("SHA512_96", np.frombuffer(b"".join(msgs), dtype=np.uint32))
+    for m, w in zip(msgs, out):
+        assert w.tobytes() == hashlib.sha512(m).digest()
+
+
+def check_glv(U, n=500, seed=6):
+    """GLV split, as the reference's CPU-side test src/curve_algos/secp256k1_mul.rs:38-94"""
+    rng = random.Random(seed)
+    ks = [(rand256(rng) % o.K1.n,) for _ in range(n)] + [(0,), (1,), (o.K1.n - 1,), (o.K1_LAMBDA,), (2**256 - 1,)]
+    for (k,), w in zip(ks, U.run("K1_GLV", ks)):
+        k1, k2 = from_words(w[0:5]), from_words(w[5:10])
+        if w[10]:
+            k1 = -k1
+        if w[11]:
+            k2 = -k2
+        assert (k1 + k2 * o.K1_LAMBDA - k) % o.K1.n == 0 and abs(k1) < 2**128 and abs(k2) < 2**128
+
+
+def _affine_ed(P):
+    zi = pow(P[2], o.ED_P - 2, o.ED_P)
+    return P[0] * zi % o.ED_P, P[1] * zi % o.ED_P
+
+
+def check_curves(U, n=12, seed=7):
+    rng = random.Random(seed)
+    # the Strauss-Shamir corner case the reference keeps commented out (src/tests/secp256k1_curve.rs:691-741):
+    # x*G + y*B where an intermediate sum hits the point at infinity
+    x = 0x8CE48A1B5F7942ED63C3F5380D98BD57F702AA6DED0E8022B4890762ACA5FA5D
+    y = 0x84023F2E9587339FE4076DE927D8F1CBFF4279A6982E1B0599221E20153F147A
+    bx = 57955212013049338432744149260690748736552621582696778344469660993364486735760
+    by = 18014696949887157897072847726343716132385694929890630512424732633979399864330
+    w = U.run("K1_DOUBLE_MUL", [(x, y, bx, by)])[0]
+    G = (o.K1.gx, o.K1.gy)
+    exp = o.sw_add(o.K1, o.sw_mul(o.K1, x, G), o.sw_mul(o.K1, y, (bx, by)))
+    assert w[16] == 0 and (from_words(w[:8]), from_words(w[8:16])) == exp
+    for name, c in (("K1", o.K1), ("R1", o.R1)):
+        G = (c.gx, c.gy)
+        items, exps = [], []
+        for i in range(n):
+            k = rng.getrandbits(256) % c.n
+            P = o.sw_mul(c, rng.getrandbits(256) % (c.n - 1) + 1, G)
+            k = [0, 1, c.n - 1, 2, 8, 9, c.n // 2][i] if i < 7 else k
+            items.append((k, P[0], P[1]))
+            exps.append(o.sw_mul(c, k, P))
+        for e, w in zip(exps, U.run(name + "_MULPT", items)):
+            if e is None:
+                assert w[16] == 1
+            else:
+                assert w[16] == 0 and (from_words(w[:8]), from_words(w[8:16])) == e
+        items, exps = [], []
+        for i in range(n):
+            u1, u2 = rng.getrandbits(256) % c.n, rng.getrandbits(256) % c.n
+            kk = rng.getrandbits(256) % (c.n - 1) + 1
+            if i == 0:
+                kk = 1  # R = G
+            if i == 1:
+                kk = c.n - 1  # R = -G
+            if i == 2:
+                u1, u2, kk = 5, 5, c.n - 1  # u1*G + u2*(-G) = infinity
+            if i == 3:
+                u2 = 0
+            if i == 4:
+                u1 = 0
+            P = o.sw_mul(c, kk, G)
+            items.append((u1, u2, P[0], P[1]))
+            exps.append(o.sw_add(c, o.sw_mul(c, u1, G), o.sw_mul(c, u2, P)))
+        for e, w in zip(exps, U.run(name + "_DOUBLE_MUL", items)):
+            if e is None:
+                assert w[16] == 1
+            else:
+                assert w[16] == 0 and (from_words(w[:8]), from_words(w[8:16])) == e
+    items, exps = [], []
+    for i in range(n):
+        k = rng.getrandbits(256) % o.ED_L
+        px, py = _affine_ed(o.ed_mul(rng.getrandbits(256) % o.ED_L, o.ED_B))
+        k = [0, 1, 2**256 - 1, 8][i] if i < 4 else k
+        items.append((k, px, py))
+        exps.append(_affine_ed(o.ed_mul(k, (px, py, 1, px * py % o.ED_P))))
+    for e, w in zip(exps, U.run("ED_MULPT", items)):
+        assert (from_words(w[:8]), from_words(w[8:16])) == e
+
+
+def ecdsa_cases(c, nvalid=40):
+    cases = o.ecdsa_edge_cases(c)
+    for i in range(nvalid):
+        s, m, _ = o.gen_ecdsa_valid(c, i, low_s=(i % 2 == 0))
+        cases.append((f"valid{i}", s, m))
+    return cases
+
+
+def ed_cases(nvalid=40):
+    cases = o.ed25519_edge_cases()
+    for i in range(nvalid):
+        s, m, pk = o.gen_ed25519_valid(i)
+        cases.append((f"valid{i}", s, m, pk))
+    return cases
+
+
+def check_ecrecover_against_oracle(c, cases, out, status):
+    for (lab, s, m), ob, sb in zip(cases, out, status):
+        exp = o.ecrecover(c, s, m)
+        if exp is None:
+            assert sb == 1 and not ob.any(), (c.name, lab)
+        else:
+            assert sb == 0 and ob.tobytes() == exp, (c.name, lab)
+
+
+def check_ed_against_oracle(cases, valid):
+    for (lab, s, m, pk), v in zip(cases, valid):
+        assert bool(v) == o.ecverify_ed25519(s, m, pk), lab

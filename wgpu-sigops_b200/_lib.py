@@ -1,0 +1,65 @@
+"""ctypes loader for libsigops.so (the C ABI in include/sigops.h).
+
+There is no fallback: if the library is missing or cannot be loaded the import fails loudly, and every compute
+entry point raises ShaderFailureError when the C call returns nonzero (e.g. no CUDA device).
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsigops.so")
+
+# every symbol include/sigops.h declares
+SYMBOLS = [
+    "sigops_init", "sigops_shutdown", "sigops_num_devices", "sigops_last_error",
+    "sigops_secp256k1_ecrecover", "sigops_secp256r1_ecrecover", "sigops_ed25519_ecverify",
+    "sigops_precompute_bases", "sigops_last_timing", "sigops_kernel_launches",
+    "sigops_host_alloc", "sigops_host_free",
+    "sigops_secp256k1_ecrecover_device", "sigops_secp256r1_ecrecover_device", "sigops_ed25519_ecverify_device",
+    "sigops_test_unit", "sigops_test_unit_shape", "sigops_imad_peak",
+]
+
+_lib = None
+
+
+class ShaderFailureError(Exception):
+    """Mirror of the reference's `ShaderFailureError` (src/lib.rs:12-14): the device path did not complete."""
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, sz, i32, u32p = c.c_void_p, c.c_size_t, c.c_int, c.POINTER(c.c_uint32)
+    lib.sigops_init.argtypes = [c.POINTER(c.c_int), i32]
+    lib.sigops_last_error.restype = c.c_char_p
+    lib.sigops_secp256k1_ecrecover.argtypes = [vp, vp, sz, vp, vp]
+    lib.sigops_secp256r1_ecrecover.argtypes = [vp, vp, sz, vp, vp]
+    lib.sigops_ed25519_ecverify.argtypes = [vp, vp, vp, sz, vp]
+    lib.sigops_precompute_bases.argtypes = [i32, c.c_uint32, vp, c.POINTER(sz)]
+    lib.sigops_last_timing.argtypes = [c.POINTER(c.c_double)] * 3
+    lib.sigops_kernel_launches.restype = c.c_uint64
+    lib.sigops_host_alloc.argtypes = [sz]
+    lib.sigops_host_alloc.restype = vp
+    lib.sigops_host_free.argtypes = [vp]
+    lib.sigops_host_free.restype = None
+    lib.sigops_secp256k1_ecrecover_device.argtypes = [vp, vp, sz, vp, vp, vp]
+    lib.sigops_secp256r1_ecrecover_device.argtypes = [vp, vp, sz, vp, vp, vp]
+    lib.sigops_ed25519_ecverify_device.argtypes = [vp, vp, vp, sz, vp, vp]
+    lib.sigops_test_unit.argtypes = [i32, vp, sz, vp]
+    lib.sigops_test_unit_shape.argtypes = [i32, c.POINTER(i32), c.POINTER(i32)]
+    lib.sigops_imad_peak.argtypes = [i32, i32, c.POINTER(c.c_double), c.POINTER(c.c_double)]
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise ShaderFailureError(load().sigops_last_error().decode() or f"sigops error {rc}")

@@ -16,9 +16,18 @@
 #if defined(__CUDACC__)
 #define SG_HD __host__ __device__ __forceinline__
 #define SG_D __device__ __forceinline__
+// field multiplication / squaring bodies are real functions (one copy per field): the fused kernels call them
+// several thousand times per signature from a few hundred sites; inlining every site costs ~40k SASS instructions
+// per kernel (I-cache thrash, 15 min ptxas).  Within one translation unit ptxas passes the 8+8 limbs in registers.
+#if defined(SG_INLINE_FIELD)
+#define SG_CALL __host__ __device__ __forceinline__
+#else
+#define SG_CALL __host__ __device__ __noinline__
+#endif
 #else
 #define SG_HD inline
 #define SG_D inline
+#define SG_CALL inline
 #endif
 
 #if defined(__CUDA_ARCH__)

@@ -89,15 +89,32 @@ struct Sc {
         select8(r, (top != 0) || (bw == 0), s, u);
     }
     // Montgomery product a*b/R mod m; requires a < 2^256, b < m (or a*b < 2^256*m)
-    static SG_HD void mmul(u32* r, const u32* a, const u32* b) {
+    static SG_CALL Fe mmul_(Fe a, Fe b) {
         u32 t[16];
-        mul8x8(t, a, b);
-        reduce16(r, t);
+        Fe r;
+        mul8x8(t, a.v, b.v);
+        reduce16(r.v, t);
+        return r;
+    }
+    static SG_CALL Fe msqr_(Fe a) {
+        u32 t[16];
+        Fe r;
+        sqr8(t, a.v);
+        reduce16(r.v, t);
+        return r;
+    }
+    static SG_HD void mmul(u32* r, const u32* a, const u32* b) {
+        Fe x, y;
+        copy8(x.v, a);
+        copy8(y.v, b);
+        Fe z = mmul_(x, y);
+        copy8(r, z.v);
     }
     static SG_HD void msqr(u32* r, const u32* a) {
-        u32 t[16];
-        sqr8(t, a);
-        reduce16(r, t);
+        Fe x;
+        copy8(x.v, a);
+        Fe z = msqr_(x);
+        copy8(r, z.v);
     }
     static SG_HD void to_mont(u32* r, const u32* a) {
         u32 r2[8];

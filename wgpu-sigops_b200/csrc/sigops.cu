@@ -1,0 +1,539 @@
+// libsigops host layer: persistent device pool, contiguous sharding across GPUs, pinned-aware transfers and the
+// extern "C" entry points declared in include/sigops.h.
+//
+// Replaces src/gpu.rs:5-170 (per-call wgpu device creation, storage/uniform buffers, pipeline creation from a WGSL
+// string, dispatch, staging-buffer read-back and device.destroy()) and the host halves of
+// src/secp256k1_ecdsa.rs:11-213, src/secp256r1_ecdsa.rs:12-214, src/ed25519_eddsa.rs:12-257 (flatten, zero-pad to a
+// power of two, five to seven dispatches, slice the padded result).  Here: no padding, one kernel launch per shard,
+// device context and buffers persist across calls, and there is no collective -- shards are independent
+// (SURVEY.md 8e).  There is no CPU fallback: without a CUDA device every compute entry point returns nonzero.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace sigops;
+
+namespace {
+
+std::mutex g_mu;
+std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+void set_err(const std::string& s) { g_err = s; }
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            char b_[512];                                                                              \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            set_err(b_);                                                                               \
+            return 1;                                                                                  \
+        }                                                                                              \
+    } while (0)
+
+struct Device {
+    int id = -1;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // device buffers (grow-only)
+    uint8_t* d_in = nullptr;
+    size_t in_cap = 0;
+    uint8_t* d_out = nullptr;
+    size_t out_cap = 0;
+    Q4* scratch = nullptr;
+    size_t scratch_cap = 0;  // in Q4
+    const u32 *k1g = nullptr, *r1g = nullptr, *edb = nullptr;
+    int grid_k1 = 0, grid_r1 = 0, grid_ed = 0, grid_unit = 0;
+    float ms_h2d = 0, ms_kernel = 0, ms_d2h = 0;
+};
+
+std::vector<Device> g_dev;
+bool g_inited = false;
+
+int ensure_buf(uint8_t** p, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) CK(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    size_t want = need + need / 4 + 4096;
+    CK(cudaMalloc((void**)p, want));
+    *cap = want;
+    return 0;
+}
+
+int ensure_scratch(Device& d, size_t q4s) {
+    if (q4s <= d.scratch_cap) return 0;
+    if (d.scratch) CK(cudaFree(d.scratch));
+    d.scratch = nullptr;
+    d.scratch_cap = 0;
+    CK(cudaMalloc((void**)&d.scratch, q4s * sizeof(Q4)));
+    d.scratch_cap = q4s;
+    return 0;
+}
+
+template <class K>
+int max_grid(Device& d, K kernel, int* out) {
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0));
+    if (per_sm < 1) per_sm = 1;
+    *out = per_sm * d.sms;
+    return 0;
+}
+
+int init_device(Device& d, int id) {
+    d.id = id;
+    CK(cudaSetDevice(id));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, id));
+    if (prop.major < 10) {
+        char b[256];
+        snprintf(b, sizeof b, "device %d (%s) is sm_%d%d; libsigops is built for sm_100a only", id, prop.name, prop.major,
+                 prop.minor);
+        set_err(b);
+        return 1;
+    }
+    d.sms = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    for (auto& e : d.ev) CK(cudaEventCreate(&e));
+    void* p = nullptr;
+    CK(cudaGetSymbolAddress(&p, k1_gtab));
+    d.k1g = (const u32*)p;
+    CK(cudaGetSymbolAddress(&p, r1_gtab));
+    d.r1g = (const u32*)p;
+    CK(cudaGetSymbolAddress(&p, ed_btab));
+    d.edb = (const u32*)p;
+    if (max_grid(d, ecrecover_kernel<CurveK1>, &d.grid_k1)) return 1;
+    if (max_grid(d, ecrecover_kernel<CurveR1>, &d.grid_r1)) return 1;
+    if (max_grid(d, ed25519_verify_kernel, &d.grid_ed)) return 1;
+    if (max_grid(d, unit_kernel, &d.grid_unit)) return 1;
+    return 0;
+}
+
+int do_init(const int* ids, int n) {
+    if (g_inited) return 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_err(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                "); libsigops has no CPU fallback");
+        return 2;
+    }
+    std::vector<int> use;
+    if (ids && n > 0) {
+        for (int i = 0; i < n; i++) {
+            if (ids[i] < 0 || ids[i] >= count) {
+                set_err("sigops_init: device id out of range");
+                return 1;
+            }
+            use.push_back(ids[i]);
+        }
+    } else {
+        int want = count;
+        if (const char* s = getenv("SIGOPS_GPUS")) {
+            int v = atoi(s);
+            if (v >= 1 && v < want) want = v;
+        }
+        for (int i = 0; i < want; i++) use.push_back(i);
+    }
+    g_dev.assign(use.size(), Device());
+    for (size_t i = 0; i < use.size(); i++)
+        if (init_device(g_dev[i], use[i])) {
+            g_dev.clear();
+            return 1;
+        }
+    g_inited = true;
+    return 0;
+}
+
+// device context for the CURRENT device (used by the *_device entry points and the test shims)
+Device* current_device() {
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) return nullptr;
+    for (auto& d : g_dev)
+        if (d.id == cur) return &d;
+    return nullptr;
+}
+
+enum Op { OP_K1 = 0, OP_R1 = 1, OP_ED = 2 };
+
+int launch_op(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_msgs, const uint8_t* d_pks, size_t n,
+              uint8_t* d_out, uint8_t* d_status, cudaStream_t st) {
+    if (n == 0) return 0;
+    int max_g = op == OP_K1 ? d.grid_k1 : op == OP_R1 ? d.grid_r1 : d.grid_ed;
+    size_t blocks = (n + kBlock - 1) / kBlock;
+    int grid = (int)std::min<size_t>(blocks, (size_t)max_g);
+    size_t chunks = op == OP_ED ? kEdTabChunks : kSwTabChunks;
+    if (ensure_scratch(d, chunks * (size_t)max_g * kBlock)) return 1;
+    switch (op) {
+        case OP_K1:
+            ecrecover_kernel<CurveK1><<<grid, kBlock, 0, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, n, (Q4*)d_out,
+                                                              d_status, d.scratch, d.k1g);
+            break;
+        case OP_R1:
+            ecrecover_kernel<CurveR1><<<grid, kBlock, 0, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, n, (Q4*)d_out,
+                                                              d_status, d.scratch, d.r1g);
+            break;
+        case OP_ED:
+            ed25519_verify_kernel<<<grid, kBlock, 0, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, (const Q4*)d_pks, n,
+                                                           d_out, d.scratch, d.edb);
+            break;
+    }
+    CK(cudaGetLastError());
+    g_launches++;
+    return 0;
+}
+
+// one shard on one device: H2D -> kernel -> D2H on the device's stream, timed with events
+int run_shard(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n, uint8_t* out,
+              uint8_t* status) {
+    CK(cudaSetDevice(d.id));
+    const size_t in_bytes = n * (op == OP_ED ? 128 : 96);
+    const size_t out_main = op == OP_ED ? n : n * 64;
+    const size_t out_bytes = op == OP_ED ? n : n * 65;
+    if (ensure_buf(&d.d_in, &d.in_cap, in_bytes + 64)) return 1;
+    if (ensure_buf(&d.d_out, &d.out_cap, out_bytes + 64)) return 1;
+    uint8_t* d_sigs = d.d_in;
+    uint8_t* d_msgs = d.d_in + n * 64;
+    uint8_t* d_pks = d.d_in + n * 96;
+    CK(cudaEventRecord(d.ev[0], d.stream));
+    CK(cudaMemcpyAsync(d_sigs, sigs, n * 64, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(d_msgs, msgs, n * 32, cudaMemcpyHostToDevice, d.stream));
+    if (op == OP_ED) CK(cudaMemcpyAsync(d_pks, pks, n * 32, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaEventRecord(d.ev[1], d.stream));
+    uint8_t* d_status = op == OP_ED ? nullptr : d.d_out + n * 64;
+    if (launch_op(d, op, d_sigs, d_msgs, d_pks, n, d.d_out, d_status, d.stream)) return 1;
+    CK(cudaEventRecord(d.ev[2], d.stream));
+    CK(cudaMemcpyAsync(out, d.d_out, out_main, cudaMemcpyDeviceToHost, d.stream));
+    if (op != OP_ED && status) CK(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaEventRecord(d.ev[3], d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    CK(cudaEventElapsedTime(&d.ms_h2d, d.ev[0], d.ev[1]));
+    CK(cudaEventElapsedTime(&d.ms_kernel, d.ev[1], d.ev[2]));
+    CK(cudaEventElapsedTime(&d.ms_d2h, d.ev[2], d.ev[3]));
+    return 0;
+}
+
+// below this many signatures per device a shard is not worth a GPU of its own (launch + sync latency dominates)
+constexpr size_t kMinShard = 4096;
+
+int run_batch(Op op, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n, uint8_t* out,
+              uint8_t* status) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (n == 0) return 0;
+    if (!sigs || !msgs || !out || (op == OP_ED && !pks)) {
+        set_err("null buffer");
+        return 1;
+    }
+    if (int rc = do_init(nullptr, 0)) return rc;
+    for (auto& d : g_dev) d.ms_h2d = d.ms_kernel = d.ms_d2h = 0;
+    size_t G = std::min<size_t>(g_dev.size(), (n + kMinShard - 1) / kMinShard);
+    if (G < 1) G = 1;
+    const size_t out_stride = op == OP_ED ? 1 : 64;
+    if (G == 1) return run_shard(g_dev[0], op, sigs, msgs, pks, n, out, status);
+    std::vector<int> rcs(G, 0);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; g++) {
+        size_t lo = g * n / G, hi = (g + 1) * n / G;  // contiguous shard [lo, hi)
+        th.emplace_back([&, g, lo, hi]() {
+            rcs[g] = run_shard(g_dev[g], op, sigs + lo * 64, msgs + lo * 32, pks ? pks + lo * 32 : nullptr, hi - lo,
+                               out + lo * out_stride, status ? status + lo : nullptr);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (size_t g = 0; g < G; g++)
+        if (rcs[g]) return rcs[g];  // one failed shard fails the whole call (all-or-nothing, like ShaderFailureError)
+    return 0;
+}
+
+int run_device(Op op, const void* d_sigs, const void* d_msgs, const void* d_pks, size_t n, void* d_out, void* d_status,
+               void* stream) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = do_init(nullptr, 0)) return rc;
+    Device* d = current_device();
+    if (!d) {
+        set_err("current CUDA device is not part of the sigops pool");
+        return 1;
+    }
+    return launch_op(*d, op, (const uint8_t*)d_sigs, (const uint8_t*)d_msgs, (const uint8_t*)d_pks, n, (uint8_t*)d_out,
+                     (uint8_t*)d_status, (cudaStream_t)stream);
+}
+
+// ---- precompute::*_bases (CPU only, as in the reference) ------------------------------------------------
+// 256-bit modular helpers on the portable paths of field.cuh; entry i = (i+1)*G in affine coordinates.
+template <class F>
+void to_limbs_mont(std::vector<uint32_t>& out, const Fe& coord_plain_in_F, const u32* p_limbs, int num_limbs,
+                   int log_limb_size) {
+    // value v (canonical, plain) -> v * 2^(num_limbs*log_limb_size) mod p by repeated doubling mod p
+    u32 v[8];
+    F::to_plain(v, coord_plain_in_F);
+    const int shift = num_limbs * log_limb_size;
+    for (int i = 0; i < shift; i++) {
+        u32 t[8], u[8];
+        u32 c = add8(t, v, v);
+        u32 bw = sub8(u, t, p_limbs);
+        select8(v, c != 0 || bw == 0, t, u);
+    }
+    // split into log_limb_size-bit limbs, little-endian
+    for (int l = 0; l < num_limbs; l++) {
+        uint32_t limb = 0;
+        for (int b = 0; b < log_limb_size; b++) {
+            int bit = l * log_limb_size + b;
+            if (bit < 256) limb |= ((v[bit >> 5] >> (bit & 31)) & 1u) << b;
+        }
+        out.push_back(limb);
+    }
+}
+
+int calc_num_limbs(int log_limb_size) {  // multiprecision::utils::calc_num_limbs(log_limb_size, 256)
+    int l = 256 / log_limb_size;
+    while (l * log_limb_size <= 256) l++;
+    return l;
+}
+
+template <class C>
+void sw_bases(std::vector<uint32_t>& out, const u32* gxy_table_entry0, const u32* p_limbs, int log_limb_size) {
+    typedef typename C::F F;
+    const int num_limbs = calc_num_limbs(log_limb_size);
+    Fe gx, gy;
+    F::from_table(gx, gxy_table_entry0);
+    F::from_table(gy, gxy_table_entry0 + 8);
+    JacPoint P;
+    P.inf = true;
+    for (int i = 0; i < 16; i++) {
+        jac_madd<C>(P, gx, gy);
+        Fe zi, zi2, ax, ay;
+        fe_inv((F*)0, zi, P.Z);
+        F::sqr(zi2, zi);
+        F::mul(ax, P.X, zi2);
+        F::mul(zi2, zi2, zi);
+        F::mul(ay, P.Y, zi2);
+        to_limbs_mont<F>(out, ax, p_limbs, num_limbs, log_limb_size);
+        to_limbs_mont<F>(out, ay, p_limbs, num_limbs, log_limb_size);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int sigops_init(const int* device_ids, int n_devices) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return do_init(device_ids, n_devices);
+}
+
+int sigops_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& d : g_dev) {
+        cudaSetDevice(d.id);
+        if (d.d_in) cudaFree(d.d_in);
+        if (d.d_out) cudaFree(d.d_out);
+        if (d.scratch) cudaFree(d.scratch);
+        for (auto& e : d.ev)
+            if (e) cudaEventDestroy(e);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    g_dev.clear();
+    g_inited = false;
+    return 0;
+}
+
+int sigops_num_devices(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (do_init(nullptr, 0)) return 0;
+    return (int)g_dev.size();
+}
+
+const char* sigops_last_error(void) { return g_err.c_str(); }
+
+int sigops_secp256k1_ecrecover(const uint8_t* sigs, const uint8_t* msgs, size_t n, uint8_t* out_pubkeys,
+                               uint8_t* out_status) {
+    return run_batch(OP_K1, sigs, msgs, nullptr, n, out_pubkeys, out_status);
+}
+
+int sigops_secp256r1_ecrecover(const uint8_t* sigs, const uint8_t* msgs, size_t n, uint8_t* out_pubkeys,
+                               uint8_t* out_status) {
+    return run_batch(OP_R1, sigs, msgs, nullptr, n, out_pubkeys, out_status);
+}
+
+int sigops_ed25519_ecverify(const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n,
+                            uint8_t* out_valid) {
+    return run_batch(OP_ED, sigs, msgs, pks, n, out_valid, nullptr);
+}
+
+int sigops_secp256k1_ecrecover_device(const void* d_sigs, const void* d_msgs, size_t n, void* d_out, void* d_status,
+                                      void* stream) {
+    return run_device(OP_K1, d_sigs, d_msgs, nullptr, n, d_out, d_status, stream);
+}
+int sigops_secp256r1_ecrecover_device(const void* d_sigs, const void* d_msgs, size_t n, void* d_out, void* d_status,
+                                      void* stream) {
+    return run_device(OP_R1, d_sigs, d_msgs, nullptr, n, d_out, d_status, stream);
+}
+int sigops_ed25519_ecverify_device(const void* d_sigs, const void* d_msgs, const void* d_pks, size_t n, void* d_out,
+                                   void* stream) {
+    return run_device(OP_ED, d_sigs, d_msgs, d_pks, n, d_out, nullptr, stream);
+}
+
+int sigops_last_timing(double* h2d_ms, double* kernel_ms, double* d2h_ms) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    double a = 0, b = 0, c = 0;
+    for (auto& d : g_dev) {
+        a = std::max(a, (double)d.ms_h2d);
+        b = std::max(b, (double)d.ms_kernel);
+        c = std::max(c, (double)d.ms_d2h);
+    }
+    if (h2d_ms) *h2d_ms = a;
+    if (kernel_ms) *kernel_ms = b;
+    if (d2h_ms) *d2h_ms = c;
+    return 0;
+}
+
+uint64_t sigops_kernel_launches(void) { return g_launches.load(); }
+
+void* sigops_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        set_err("cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+
+void sigops_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int sigops_precompute_bases(int curve, uint32_t log_limb_size, uint32_t* out, size_t* inout_len) {
+    if (log_limb_size < 11 || log_limb_size > 15 || !inout_len) {
+        set_err("log_limb_size must be in 11..=15");
+        return 1;
+    }
+    std::vector<uint32_t> v;
+    const int num_limbs = calc_num_limbs((int)log_limb_size);
+    if (curve == SIGOPS_CURVE_SECP256K1) {
+        const u32 P[8] = SG_K1_P;
+        sw_bases<CurveK1>(v, k1_g_host, P, (int)log_limb_size);
+    } else if (curve == SIGOPS_CURVE_SECP256R1) {
+        const u32 P[8] = SG_R1_P;
+        sw_bases<CurveR1>(v, r1_g_host, P, (int)log_limb_size);
+    } else if (curve == SIGOPS_CURVE_ED25519) {
+        const u32 P[8] = SG_ED_P;
+        Fe bx, by;
+        copy8(bx.v, ed_b_host);
+        copy8(by.v, ed_b_host + 8);
+        EdPoint acc, B;
+        B.X = bx;
+        B.Y = by;
+        FE::set_one(B.Z);
+        FE::mul(B.T, bx, by);
+        const Fe d2 = {SG_ED_D2};
+        Fe ypx, ymx, t2d;
+        FE::add(ypx, by, bx);
+        FE::sub(ymx, by, bx);
+        FE::mul(t2d, B.T, d2);
+        ed_set_identity(acc);
+        for (int i = 0; i < 16; i++) {
+            ed_add_niels(acc, ypx, ymx, t2d, false, true);
+            Fe zi, ax, ay, at;
+            fe_inv((FE*)0, zi, acc.Z);
+            FE::mul(ax, acc.X, zi);
+            FE::mul(ay, acc.Y, zi);
+            FE::mul(at, ax, ay);
+            to_limbs_mont<FE>(v, ax, P, num_limbs, (int)log_limb_size);
+            to_limbs_mont<FE>(v, ay, P, num_limbs, (int)log_limb_size);
+            to_limbs_mont<FE>(v, at, P, num_limbs, (int)log_limb_size);
+        }
+    } else {
+        set_err("unknown curve");
+        return 1;
+    }
+    if (!out || *inout_len < v.size()) {
+        *inout_len = v.size();
+        if (out) {
+            set_err("output buffer too small");
+            return 1;
+        }
+        return 0;
+    }
+    memcpy(out, v.data(), v.size() * sizeof(uint32_t));
+    *inout_len = v.size();
+    return 0;
+}
+
+int sigops_test_unit_shape(int op, int* in_words, int* out_words) {
+    if (op < 0 || op >= SIGOPS_UNIT_COUNT || !in_words || !out_words) return 1;
+    unit_shape(op, *in_words, *out_words);
+    return 0;
+}
+
+int sigops_test_unit(int op, const uint32_t* in, size_t n, uint32_t* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (op < 0 || op >= SIGOPS_UNIT_COUNT) {
+        set_err("bad unit op");
+        return 1;
+    }
+    if (n == 0) return 0;
+    if (int rc = do_init(nullptr, 0)) return rc;
+    Device& d = g_dev[0];
+    CK(cudaSetDevice(d.id));
+    int in_w, out_w;
+    unit_shape(op, in_w, out_w);
+    if (ensure_buf(&d.d_in, &d.in_cap, n * in_w * 4)) return 1;
+    if (ensure_buf(&d.d_out, &d.out_cap, n * out_w * 4)) return 1;
+    if (ensure_scratch(d, (size_t)kEdTabChunks * d.grid_unit * kBlock)) return 1;
+    CK(cudaMemcpyAsync(d.d_in, in, n * in_w * 4, cudaMemcpyHostToDevice, d.stream));
+    int grid = (int)std::min<size_t>((n + kBlock - 1) / kBlock, (size_t)d.grid_unit);
+    unit_kernel<<<grid, kBlock, 0, d.stream>>>(op, (const u32*)d.d_in, n, (u32*)d.d_out, d.scratch, d.k1g, d.r1g, d.edb);
+    CK(cudaGetLastError());
+    g_launches++;
+    CK(cudaMemcpyAsync(out, d.d_out, n * out_w * 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    return 0;
+}
+
+int sigops_imad_peak(int kind, int iters, double* ops_per_sec, double* ms_out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = do_init(nullptr, 0)) return rc;
+    Device& d = g_dev[0];
+    CK(cudaSetDevice(d.id));
+    if (ensure_buf(&d.d_out, &d.out_cap, (size_t)d.sms * 8 * 256 * 4)) return 1;
+    const int grid = d.sms * 8, block = 256;  // 2048 threads per SM: full occupancy
+    double per_thread_iter;
+    for (int rep = 0; rep < 2; rep++) {  // first pass warms up
+        CK(cudaEventRecord(d.ev[0], d.stream));
+        switch (kind) {
+            case 0: imad_peak_kernel<0><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
+            case 1: imad_peak_kernel<1><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
+            case 2: imad_peak_kernel<2><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
+            case 3: imad_peak_kernel<3><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
+            case 4: imad_peak_kernel<4><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
+            default: set_err("bad kind"); return 1;
+        }
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(d.ev[1], d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+    }
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
+    // counted operations per thread per outer iteration (16 unrolled blocks):
+    //  kind 0: 8 IMAD; 1: 8 IMAD.WIDE; 2: 8 IMAD.WIDE(.X); 3: 8 IADD; 4: 8 IMAD.WIDE + 8 IADD (counted: the 8 wide)
+    per_thread_iter = 16.0 * 8.0;
+    double ops = per_thread_iter * (double)iters * (double)grid * block;
+    if (ops_per_sec) *ops_per_sec = ops / (ms * 1e-3);
+    if (ms_out) *ms_out = ms;
+    return 0;
+}
+
+}  // extern "C"
