@@ -78,6 +78,12 @@ int sigops_ed25519_ecverify(const uint8_t* sigs, const uint8_t* msgs, const uint
  * these limbs (its own 32-bit tables are baked into the library). */
 int sigops_precompute_bases(int curve, uint32_t log_limb_size, uint32_t* out, size_t* inout_len);
 
+/* Shard planner used by the host entry points (pure host logic, no device needed): the batch is cut into
+ * n_used <= n_devices contiguous ranges [bounds[g], bounds[g+1]) -- one per device, no exchange between them.  Replaces
+ * the single-adapter dispatch of src/gpu.rs:5-35 and the pow-2 grid lookup `compute_num_workgroups`
+ * (src/benchmarks/mod.rs:10-53).  bounds must hold n_devices + 1 entries. */
+int sigops_plan_shards(size_t n, int n_devices, size_t* bounds, int* n_used);
+
 /* Observability (the reference has none: `timestamp_writes: None`, src/gpu.rs:98).  Milliseconds of the
  * last host-buffer call, measured with CUDA events on each device's stream; max over the devices used. */
 int sigops_last_timing(double* h2d_ms, double* kernel_ms, double* d2h_ms);

@@ -1,0 +1,128 @@
+"""ctypes wrapper of oracle/sigops_oracle.c (TEST INFRASTRUCTURE ONLY -- see that file's header).
+
+Imported only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs.  The library
+is (re)built with `-march=native` on the machine it runs on (a stamp records the CPU model), because the build
+container and the GPU box may have different host CPUs.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_build", "liboracle.so")
+STAMP = SO + ".cpu"
+_lib = None
+
+
+def _cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(HERE, "sigops_oracle.c")
+    cpu = _cpu_model()
+    fresh = (
+        os.path.exists(SO)
+        and os.path.exists(STAMP)
+        and open(STAMP).read() == cpu
+        and os.path.getmtime(SO) >= os.path.getmtime(src)
+    )
+    if force or not fresh:
+        subprocess.check_call(["make", "-s", "-B", "-C", HERE])
+        with open(STAMP, "w") as f:
+            f.write(cpu)
+    return SO
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        lib = ctypes.CDLL(build())
+        vp, sz, i32, u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64
+        lib.oracle_ecrecover.argtypes = [i32, vp, vp, sz, vp, vp, i32]
+        lib.oracle_ed25519_verify.argtypes = [vp, vp, vp, sz, vp, i32]
+        lib.oracle_gen_ecdsa.argtypes = [i32, u64, sz, i32, vp, vp, vp, i32]
+        lib.oracle_gen_ed25519.argtypes = [u64, sz, vp, vp, vp, i32]
+        lib.oracle_sha512.argtypes = [vp, sz, vp]
+        _lib = lib
+    return _lib
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _u8(a, width):
+    if isinstance(a, (bytes, bytearray)):
+        a = np.frombuffer(bytes(a), dtype=np.uint8)
+    elif not isinstance(a, np.ndarray):
+        a = np.frombuffer(b"".join(bytes(x) for x in a), dtype=np.uint8)
+    return np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, width)
+
+
+def ecrecover(curve: int, sigs, msgs, threads: int = 0):
+    """curve 0 = secp256k1, 1 = secp256r1.  Returns (n x 64 uint8 X||Y, n uint8 status)."""
+    sigs, msgs = _u8(sigs, 64), _u8(msgs, 32)
+    n = sigs.shape[0]
+    assert msgs.shape[0] == n
+    out = np.zeros((n, 64), dtype=np.uint8)
+    st = np.zeros(n, dtype=np.uint8)
+    if n:
+        rc = load().oracle_ecrecover(curve, sigs.ctypes.data, msgs.ctypes.data, n, out.ctypes.data, st.ctypes.data,
+                                     threads or host_threads())
+        assert rc == 0
+    return out, st
+
+
+def ecverify_ed25519(sigs, msgs, pks, threads: int = 0):
+    sigs, msgs, pks = _u8(sigs, 64), _u8(msgs, 32), _u8(pks, 32)
+    n = sigs.shape[0]
+    assert msgs.shape[0] == n == pks.shape[0]
+    out = np.zeros(n, dtype=np.uint8)
+    if n:
+        rc = load().oracle_ed25519_verify(sigs.ctypes.data, msgs.ctypes.data, pks.ctypes.data, n, out.ctypes.data,
+                                          threads or host_threads())
+        assert rc == 0
+    return out
+
+
+def gen_ecdsa(curve: int, n: int, seed: int = 0x51600002, low_s: bool = True, threads: int = 0):
+    """n valid Fuel-encoded signatures: (sigs n x 64, msgs n x 32, signer public keys n x 64)."""
+    sigs = np.zeros((n, 64), dtype=np.uint8)
+    msgs = np.zeros((n, 32), dtype=np.uint8)
+    pks = np.zeros((n, 64), dtype=np.uint8)
+    if n:
+        rc = load().oracle_gen_ecdsa(curve, seed, n, int(low_s), sigs.ctypes.data, msgs.ctypes.data, pks.ctypes.data,
+                                     threads or host_threads())
+        assert rc == 0
+    return sigs, msgs, pks
+
+
+def gen_ed25519(n: int, seed: int = 0x51600002, threads: int = 0):
+    """n valid RFC 8032 signatures over 32-byte messages: (sigs n x 64, msgs n x 32, pks n x 32)."""
+    sigs = np.zeros((n, 64), dtype=np.uint8)
+    msgs = np.zeros((n, 32), dtype=np.uint8)
+    pks = np.zeros((n, 32), dtype=np.uint8)
+    if n:
+        rc = load().oracle_gen_ed25519(seed, n, sigs.ctypes.data, msgs.ctypes.data, pks.ctypes.data,
+                                       threads or host_threads())
+        assert rc == 0
+    return sigs, msgs, pks
+
+
+def sha512(msg: bytes) -> bytes:
+    out = np.zeros(64, dtype=np.uint8)
+    buf = np.frombuffer(msg, dtype=np.uint8) if msg else np.zeros(1, dtype=np.uint8)
+    assert load().oracle_sha512(buf.ctypes.data, len(msg), out.ctypes.data) == 0
+    return out.tobytes()

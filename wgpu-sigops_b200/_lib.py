@@ -7,7 +7,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsigops.so")
+# SIGOPS_LIB selects an experimental build of the same library (tools/variants.py); default = the product
+LIB_PATH = os.environ.get("SIGOPS_LIB") or os.path.join(HERE, "libsigops.so")
 
 # every symbol include/sigops.h declares
 SYMBOLS = [
@@ -16,7 +17,7 @@ SYMBOLS = [
     "sigops_precompute_bases", "sigops_last_timing", "sigops_kernel_launches",
     "sigops_host_alloc", "sigops_host_free",
     "sigops_secp256k1_ecrecover_device", "sigops_secp256r1_ecrecover_device", "sigops_ed25519_ecverify_device",
-    "sigops_test_unit", "sigops_test_unit_shape", "sigops_imad_peak",
+    "sigops_test_unit", "sigops_test_unit_shape", "sigops_imad_peak", "sigops_plan_shards",
 ]
 
 _lib = None
@@ -55,6 +56,7 @@ def load() -> ctypes.CDLL:
     lib.sigops_ed25519_ecverify_device.argtypes = [vp, vp, vp, sz, vp, vp]
     lib.sigops_test_unit.argtypes = [i32, vp, sz, vp]
     lib.sigops_test_unit_shape.argtypes = [i32, c.POINTER(i32), c.POINTER(i32)]
+    lib.sigops_plan_shards.argtypes = [sz, i32, c.POINTER(sz), c.POINTER(i32)]
     lib.sigops_imad_peak.argtypes = [i32, i32, c.POINTER(c.c_double), c.POINTER(c.c_double)]
     _lib = lib
     return lib

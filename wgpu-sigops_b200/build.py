@@ -27,12 +27,13 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = None, extra=()) -> str:
+    """Default: the product library.  `out` / `extra` build an experimental variant (tools/variants.py) elsewhere."""
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "sigops.cu"), "-lcudart"]
-    log = os.path.join(HERE, "build.log")
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-o", out or LIB, os.path.join(CSRC, "sigops.cu"), "-lcudart"]
+    log = (out + ".log") if out else os.path.join(HERE, "build.log")
     with open(log, "w") as f:
         rc = subprocess.call(cmd, stdout=f, stderr=subprocess.STDOUT)
     if rc != 0:
@@ -40,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building libsigops.so (see %s)" % log)
     if verbose:
         sys.stdout.write(open(log).read())
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -12,7 +12,17 @@
 
 namespace sigops {
 
-static constexpr int kBlock = 128;
+#ifndef SG_BLOCK
+#define SG_BLOCK 128
+#endif
+static constexpr int kBlock = SG_BLOCK;
+// minimum resident blocks per SM the register allocation must allow (occupancy knob)
+#ifndef SG_MINB_SW
+#define SG_MINB_SW 1
+#endif
+#ifndef SG_MINB_ED
+#define SG_MINB_ED 1
+#endif
 
 #if defined(__CUDACC__)
 
@@ -25,7 +35,7 @@ __device__ __forceinline__ void stage_table(u32* dst, const u32* src, int words)
 }
 
 template <class C>
-__global__ void __launch_bounds__(kBlock) ecrecover_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
+__global__ void __launch_bounds__(kBlock, SG_MINB_SW) ecrecover_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
                                                            size_t n, Q4* __restrict__ out, uint8_t* __restrict__ status,
                                                            Q4* __restrict__ scratch, const u32* __restrict__ gtab_g) {
     __shared__ __align__(16) u32 gtab[SG_GTAB_ENTRIES * 16];
@@ -63,7 +73,7 @@ __global__ void __launch_bounds__(kBlock) ecrecover_kernel(const Q4* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(kBlock) ed25519_verify_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
+__global__ void __launch_bounds__(kBlock, SG_MINB_ED) ed25519_verify_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
                                                                 const Q4* __restrict__ pks, size_t n,
                                                                 uint8_t* __restrict__ valid, Q4* __restrict__ scratch,
                                                                 const u32* __restrict__ btab_g) {

@@ -228,6 +228,15 @@ int run_shard(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs, const 
 // below this many signatures per device a shard is not worth a GPU of its own (launch + sync latency dominates)
 constexpr size_t kMinShard = 4096;
 
+// Shard planner: G_eff = min(G, ceil(n / kMinShard)) devices, device g gets the contiguous range
+// [floor(g*n/G_eff), floor((g+1)*n/G_eff)).  bounds receives G_eff + 1 entries.  Pure host logic.
+int plan_shards(size_t n, int n_devices, size_t* bounds) {
+    size_t G = std::min<size_t>((size_t)std::max(n_devices, 1), (n + kMinShard - 1) / kMinShard);
+    if (G < 1) G = 1;
+    for (size_t g = 0; g <= G; g++) bounds[g] = g * n / G;  // n <= 2^30 (src/secp256k1_ecdsa.rs:22): no overflow
+    return (int)G;
+}
+
 int run_batch(Op op, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n, uint8_t* out,
               uint8_t* status) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -238,15 +247,14 @@ int run_batch(Op op, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pk
     }
     if (int rc = do_init(nullptr, 0)) return rc;
     for (auto& d : g_dev) d.ms_h2d = d.ms_kernel = d.ms_d2h = 0;
-    size_t G = std::min<size_t>(g_dev.size(), (n + kMinShard - 1) / kMinShard);
-    if (G < 1) G = 1;
+    std::vector<size_t> bounds(g_dev.size() + 1);
+    const size_t G = (size_t)plan_shards(n, (int)g_dev.size(), bounds.data());
     const size_t out_stride = op == OP_ED ? 1 : 64;
     if (G == 1) return run_shard(g_dev[0], op, sigs, msgs, pks, n, out, status);
     std::vector<int> rcs(G, 0);
-    std::vector<std::string> errs(G);
     std::vector<std::thread> th;
     for (size_t g = 0; g < G; g++) {
-        size_t lo = g * n / G, hi = (g + 1) * n / G;  // contiguous shard [lo, hi)
+        const size_t lo = bounds[g], hi = bounds[g + 1];  // contiguous shard [lo, hi)
         th.emplace_back([&, g, lo, hi]() {
             rcs[g] = run_shard(g_dev[g], op, sigs + lo * 64, msgs + lo * 32, pks ? pks + lo * 32 : nullptr, hi - lo,
                                out + lo * out_stride, status ? status + lo : nullptr);
@@ -384,6 +392,15 @@ int sigops_secp256r1_ecrecover_device(const void* d_sigs, const void* d_msgs, si
 int sigops_ed25519_ecverify_device(const void* d_sigs, const void* d_msgs, const void* d_pks, size_t n, void* d_out,
                                    void* stream) {
     return run_device(OP_ED, d_sigs, d_msgs, d_pks, n, d_out, nullptr, stream);
+}
+
+int sigops_plan_shards(size_t n, int n_devices, size_t* bounds, int* n_used) {
+    if (!bounds || !n_used || n_devices < 1) {
+        set_err("sigops_plan_shards: bad arguments");
+        return 1;
+    }
+    *n_used = plan_shards(n, n_devices, bounds);
+    return 0;
 }
 
 int sigops_last_timing(double* h2d_ms, double* kernel_ms, double* d2h_ms) {
