@@ -123,7 +123,7 @@ enum {
     SIGOPS_UNIT_K1_SQR = 1,    /* in 8                         out 8                                   */
     SIGOPS_UNIT_K1_ADD = 2,    /* in 16                        out 8                                   */
     SIGOPS_UNIT_K1_SUB = 3,    /* in 16                        out 8                                   */
-    SIGOPS_UNIT_K1_INV = 4,    /* in 8                         out 8  : a^(p-2)                        */
+    SIGOPS_UNIT_K1_INV = 4,    /* in 8                         out 8  : a^-1 mod p (safegcd), 0 -> 0    */
     SIGOPS_UNIT_K1_SQRT = 5,   /* in 8                         out 8  : a^((p+1)/4)                    */
     SIGOPS_UNIT_R1_MUL = 6,    /* plain in, plain out (through Montgomery form)                        */
     SIGOPS_UNIT_R1_SQR = 7,
@@ -151,7 +151,11 @@ enum {
     SIGOPS_UNIT_ED_MULPT = 29,      /* in 24 (k, x, y)         out 16 : k*(x,y) affine x,y             */
     SIGOPS_UNIT_K1_DOUBLE_MUL = 30, /* in 32 (u1,u2,x,y)       out 17 : u1*G + u2*(x,y)                */
     SIGOPS_UNIT_R1_DOUBLE_MUL = 31,
-    SIGOPS_UNIT_COUNT = 32
+    SIGOPS_UNIT_K1N_INV_FERMAT = 32, /* in 8                    out 8  : a^(n-2) mod n (cross-check of the safegcd path) */
+    SIGOPS_UNIT_K1_INV_FERMAT = 33,
+    SIGOPS_UNIT_R1_INV_FERMAT = 34,
+    SIGOPS_UNIT_ED_INV_FERMAT = 35,
+    SIGOPS_UNIT_COUNT = 36
 };
 
 #ifdef __cplusplus

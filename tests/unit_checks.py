@@ -42,19 +42,31 @@ def check_wide(U, nrand=1500, seed=2):
         assert from_words(w) == a * a
 
 
+def _inv_inputs(rng, m, n):
+    xs = [rand256(rng) % m for _ in range(n)]
+    xs += [0, 1, 2, 3, m - 1, m - 2, (m + 1) // 2, (m - 1) // 2, 2**255 % m, 2**128, 2**30, 2**30 - 1, 2**60 + 1, m >> 1, m >> 30]
+    xs += [pow(2, k, m) for k in (29, 31, 59, 61, 239, 241, 255)]
+    xs += [(m - pow(2, k, m)) % m for k in (1, 30, 60, 240)]
+    return [(x % m,) for x in xs]
+
+
 def check_chains(U, n=40, seed=3):
-    """addition chains: inverse, square root ((p+1)/4 as in src/tests/mont.rs:138-175), (p-5)/8"""
+    """inverses (safegcd, cross-checked against the Fermat ladder), square root ((p+1)/4 as in
+    src/tests/mont.rs:138-175), (p-5)/8"""
     rng = random.Random(seed)
+    for prefix, p in (("K1", o.K1.p), ("R1", o.R1.p), ("ED", o.ED_P)):
+        xs = _inv_inputs(rng, p, 4 * n)
+        for (a,), w in zip(xs, U.run(prefix + "_INV", xs)):
+            assert from_words(w) == pow(a, p - 2, p), (prefix, hex(a))
+        xs = xs[: n // 2] + xs[-24:]
+        for (a,), w in zip(xs, U.run(prefix + "_INV_FERMAT", xs)):
+            assert from_words(w) == pow(a, p - 2, p), (prefix, hex(a))
     for prefix, p in (("K1", o.K1.p), ("R1", o.R1.p)):
         xs = [(rand256(rng) % p,) for _ in range(n)] + [(1,), (2,), (p - 1,)]
-        for (a,), w in zip(xs, U.run(prefix + "_INV", xs)):
-            assert from_words(w) == pow(a, p - 2, p)
         for (a,), w in zip(xs, U.run(prefix + "_SQRT", xs)):
             assert from_words(w) == pow(a, (p + 1) // 4, p)
     p = o.ED_P
     xs = [(rand256(rng) % p,) for _ in range(n)] + [(1,), (2,), (p - 1,), (0,)]
-    for (a,), w in zip(xs, U.run("ED_INV", xs)):
-        assert from_words(w) == pow(a, p - 2, p)
     for (a,), w in zip(xs, U.run("ED_POW_P58", xs)):
         assert from_words(w) == pow(a, (p - 5) // 8, p)
 
@@ -65,9 +77,12 @@ def check_scalar(U, n=300, ninv=20, seed=4):
         pairs = [(rand256(rng) % m, rand256(rng) % m) for _ in range(n)] + [(m - 1, m - 1), (0, 5), (1, 1)]
         for (a, b), w in zip(pairs, U.run(prefix + "_MUL", pairs)):
             assert from_words(w) == a * b % m
-        xs = [(rand256(rng) % m,) for _ in range(ninv)] + [(1,), (m - 1,)]
+        xs = _inv_inputs(rng, m, ninv)
         for (a,), w in zip(xs, U.run(prefix + "_INV", xs)):
             assert from_words(w) == pow(a, m - 2, m), (prefix, hex(a))
+    xs = _inv_inputs(rng, o.K1.n, 4)
+    for (a,), w in zip(xs, U.run("K1N_INV_FERMAT", xs)):
+        assert from_words(w) == pow(a, o.K1.n - 2, o.K1.n)
     xs = [(rng.getrandbits(512),) for _ in range(n)] + [(2**512 - 1,), (0,), (o.ED_L,), (o.ED_L << 256,), (o.ED_L - 1,)]
     for (a,), w in zip(xs, U.run("EDL_REDUCE512", xs, widths=[16])):
         assert from_words(w) == a % o.ED_L

@@ -142,6 +142,7 @@ SG_HD void ed_set_identity(EdPoint& P) {
 }
 
 // dbl-2008-hwcd: 4S + 3M (+1M for T when the next operation is an addition)
+template <class FE>
 SG_HD void ed_dbl(EdPoint& P, bool need_t) {
     Fe A, B, C, E, G, F, H, t;
     FE::sqr(A, P.X);
@@ -163,6 +164,7 @@ SG_HD void ed_dbl(EdPoint& P, bool need_t) {
 }
 
 // P += (or -=) Q given in cached form (Y2+X2, Y2-X2, Z2, 2d*T2): add-2008-hwcd-3, 8M (+... T optional)
+template <class FE>
 SG_HD void ed_add_cached(EdPoint& P, const Fe& ypx, const Fe& ymx, const Fe& z2, const Fe& t2d, bool negq, bool need_t) {
     Fe A, B, C, D, E, F, G, H, t;
     FE::sub(t, P.Y, P.X);
@@ -188,6 +190,7 @@ SG_HD void ed_add_cached(EdPoint& P, const Fe& ypx, const Fe& ymx, const Fe& z2,
 }
 
 // same with an affine Niels entry (y+x, y-x, 2d*x*y), Z2 = 1: 7M
+template <class FE>
 SG_HD void ed_add_niels(EdPoint& P, const Fe& ypx, const Fe& ymx, const Fe& xy2d, bool negq, bool need_t) {
     Fe A, B, C, D, E, F, G, H, t;
     FE::sub(t, P.Y, P.X);
@@ -227,6 +230,7 @@ SG_HD void ed_tab_store(const TabRef& tab, int e, const EdPoint& P) {
     tab_store_fe(tab, 8 * e + 6, t);
 }
 
+template <class FE>
 SG_HD void ed_add_from_table(EdPoint& acc, const TabRef& tab, int d, bool need_t) {
     if (d == 0) return;
     int e = (d < 0 ? -d : d) - 1;
@@ -235,7 +239,7 @@ SG_HD void ed_add_from_table(EdPoint& acc, const TabRef& tab, int d, bool need_t
     tab_load_fe(ymx, tab, 8 * e + 2);
     tab_load_fe(z2, tab, 8 * e + 4);
     tab_load_fe(t2d, tab, 8 * e + 6);
-    ed_add_cached(acc, ypx, ymx, z2, t2d, d < 0, need_t);
+    ed_add_cached<FE>(acc, ypx, ymx, z2, t2d, d < 0, need_t);
 }
 
 SG_HD void ed_load_fe_words(Fe& a, const u32* w) {
@@ -245,6 +249,7 @@ SG_HD void ed_load_fe_words(Fe& a, const u32* w) {
     a.v[4] = hi.x; a.v[5] = hi.y; a.v[6] = hi.z; a.v[7] = hi.w;
 }
 
+template <class FE>
 SG_HD void ed_add_from_btab(EdPoint& acc, const u32* btab, int d, bool need_t) {
     if (d == 0) return;
     int e = (d < 0 ? -d : d) - 1;
@@ -252,7 +257,7 @@ SG_HD void ed_add_from_btab(EdPoint& acc, const u32* btab, int d, bool need_t) {
     ed_load_fe_words(ypx, btab + 24 * e);
     ed_load_fe_words(ymx, btab + 24 * e + 8);
     ed_load_fe_words(xy2d, btab + 24 * e + 16);
-    ed_add_niels(acc, ypx, ymx, xy2d, d < 0, need_t);
+    ed_add_niels<FE>(acc, ypx, ymx, xy2d, d < 0, need_t);
 }
 
 // sqrt_ratio_i (curve25519-dalek; src/wgsl/ed25519_utils.wgsl:42-88): returns whether u/v is a square and the
@@ -284,6 +289,11 @@ SG_HD bool ed_sqrt_ratio_i(Fe& r, const Fe& u, const Fe& v) {
 // Returns 1 when the signature verifies, else 0.
 SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, const TabRef& tab, const u32* btab) {
     typedef Sc<ModEdL> S;
+#if defined(SG_HOT_INLINE)
+    typedef Inl<Fp25519> FH;  // products inlined: one doubling, one cached-addition and one Niels-addition site
+#else
+    typedef Fp25519 FH;
+#endif
     // A = decompress(pk): y from the low 255 bits (not checked against p), sign bit = bit 255
     Fe y, yy, u, v, x, one;
     u32 sign = pk_w[7] >> 31;
@@ -324,24 +334,24 @@ SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, con
         FE::sub(ymx, y, x);
         FE::mul(t2d, P1.T, d2);
         P2 = P1;
-        ed_dbl(P2, true);
+        ed_dbl<FE>(P2, true);
         ed_tab_store(tab, 1, P2);
         P3 = P2;
-        ed_add_niels(P3, ypx, ymx, t2d, false, true);
+        ed_add_niels<FE>(P3, ypx, ymx, t2d, false, true);
         ed_tab_store(tab, 2, P3);
         P4 = P2;
-        ed_dbl(P4, true);
+        ed_dbl<FE>(P4, true);
         ed_tab_store(tab, 3, P4);
         T = P4;
-        ed_add_niels(T, ypx, ymx, t2d, false, true);
+        ed_add_niels<FE>(T, ypx, ymx, t2d, false, true);
         ed_tab_store(tab, 4, T);
         T = P3;
-        ed_dbl(T, true);
+        ed_dbl<FE>(T, true);
         ed_tab_store(tab, 5, T);
-        ed_add_niels(T, ypx, ymx, t2d, false, true);
+        ed_add_niels<FE>(T, ypx, ymx, t2d, false, true);
         ed_tab_store(tab, 6, T);
         T = P4;
-        ed_dbl(T, true);
+        ed_dbl<FE>(T, true);
         ed_tab_store(tab, 7, T);
     }
     // R' = [s]B + [k](-A): 64 signed 4-bit windows for k, 32 signed 8-bit windows for s, 252 shared doublings
@@ -355,14 +365,12 @@ SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, con
 #pragma unroll 1
     for (int i = 63; i >= 0; i--) {
         if (i != 63) {
-            ed_dbl(acc, false);
-            ed_dbl(acc, false);
-            ed_dbl(acc, false);
-            ed_dbl(acc, true);
+#pragma unroll 1
+            for (int d = 0; d < 4; d++) ed_dbl<FH>(acc, d == 3);
         }
         bool has_b = (i & 1) == 0;
-        ed_add_from_table(acc, tab, recode_digit<4>(kp[0], i), true);
-        if (has_b) ed_add_from_btab(acc, btab, recode_digit<8>(kp[1], i >> 1), true);
+        ed_add_from_table<FH>(acc, tab, recode_digit<4>(kp[0], i), true);
+        if (has_b) ed_add_from_btab<FH>(acc, btab, recode_digit<8>(kp[1], i >> 1), true);
     }
     // compress and compare with the signature's R bytes
     Fe zi, ax, ay;

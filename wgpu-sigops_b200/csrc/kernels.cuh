@@ -13,15 +13,17 @@
 namespace sigops {
 
 #ifndef SG_BLOCK
-#define SG_BLOCK 128
+#define SG_BLOCK 64
 #endif
 static constexpr int kBlock = SG_BLOCK;
-// minimum resident blocks per SM the register allocation must allow (occupancy knob)
+// minimum resident blocks per SM the register allocation must allow (occupancy knob).
+// Measured on B200 (profiles/r01_variants.md): 64-thread blocks x 7 (<= 128 registers, 14-16 warps/SM) beat the
+// unconstrained build (188-250 registers, 8 warps/SM) by 10-14% despite ~1 KB of spills per thread.
 #ifndef SG_MINB_SW
-#define SG_MINB_SW 1
+#define SG_MINB_SW 7
 #endif
 #ifndef SG_MINB_ED
-#define SG_MINB_ED 1
+#define SG_MINB_ED 7
 #endif
 
 #if defined(__CUDACC__)
@@ -246,18 +248,38 @@ SG_HD void unit_dispatch(int op, u32* out, const u32* in, const TabRef& tab, con
             Sc<ModR1N>::mmul(out, am, in + 8);
             break;
         }
-        case SIGOPS_UNIT_K1N_INV: {
+        case SIGOPS_UNIT_K1N_INV:
+            Sc<ModK1N>::inv_plain(out, in);
+            break;
+        case SIGOPS_UNIT_R1N_INV:
+            Sc<ModR1N>::inv_plain(out, in);
+            break;
+        case SIGOPS_UNIT_K1N_INV_FERMAT: {
             u32 am[8], im[8];
             Sc<ModK1N>::to_mont(am, in);
             Sc<ModK1N>::minv(im, am);
             Sc<ModK1N>::from_mont(out, im);
             break;
         }
-        case SIGOPS_UNIT_R1N_INV: {
-            u32 am[8], im[8];
-            Sc<ModR1N>::to_mont(am, in);
-            Sc<ModR1N>::minv(im, am);
-            Sc<ModR1N>::from_mont(out, im);
+        case SIGOPS_UNIT_K1_INV_FERMAT: {
+            Fe a, r;
+            FpK1::from_plain(a, in);
+            fe_inv_fermat((FpK1*)0, r, a);
+            FpK1::to_plain(out, r);
+            break;
+        }
+        case SIGOPS_UNIT_R1_INV_FERMAT: {
+            Fe a, r;
+            FpR1::from_plain(a, in);
+            fe_inv_fermat((FpR1*)0, r, a);
+            FpR1::to_plain(out, r);
+            break;
+        }
+        case SIGOPS_UNIT_ED_INV_FERMAT: {
+            Fe a, r;
+            Fp25519::from_plain(a, in);
+            fe_inv_fermat((Fp25519*)0, r, a);
+            Fp25519::to_plain(out, r);
             break;
         }
         case SIGOPS_UNIT_EDL_REDUCE512:
@@ -315,13 +337,13 @@ SG_HD void unit_dispatch(int op, u32* out, const u32* in, const TabRef& tab, con
             FE::add(ypx, y, x);
             FE::sub(ymx, y, x);
             FE::mul(t2d, P1.T, d2);
-            P2 = P1; ed_dbl(P2, true); ed_tab_store(tab, 1, P2);
-            P3 = P2; ed_add_niels(P3, ypx, ymx, t2d, false, true); ed_tab_store(tab, 2, P3);
-            P4 = P2; ed_dbl(P4, true); ed_tab_store(tab, 3, P4);
-            T = P4; ed_add_niels(T, ypx, ymx, t2d, false, true); ed_tab_store(tab, 4, T);
-            T = P3; ed_dbl(T, true); ed_tab_store(tab, 5, T);
-            ed_add_niels(T, ypx, ymx, t2d, false, true); ed_tab_store(tab, 6, T);
-            T = P4; ed_dbl(T, true); ed_tab_store(tab, 7, T);
+            P2 = P1; ed_dbl<FE>(P2, true); ed_tab_store(tab, 1, P2);
+            P3 = P2; ed_add_niels<FE>(P3, ypx, ymx, t2d, false, true); ed_tab_store(tab, 2, P3);
+            P4 = P2; ed_dbl<FE>(P4, true); ed_tab_store(tab, 3, P4);
+            T = P4; ed_add_niels<FE>(T, ypx, ymx, t2d, false, true); ed_tab_store(tab, 4, T);
+            T = P3; ed_dbl<FE>(T, true); ed_tab_store(tab, 5, T);
+            ed_add_niels<FE>(T, ypx, ymx, t2d, false, true); ed_tab_store(tab, 6, T);
+            T = P4; ed_dbl<FE>(T, true); ed_tab_store(tab, 7, T);
             u32 kp[9];
             for (int i = 0; i < 8; i++) kp[i] = in[i];
             kp[8] = 0;
@@ -329,9 +351,9 @@ SG_HD void unit_dispatch(int op, u32* out, const u32* in, const TabRef& tab, con
             ed_set_identity(acc);
             for (int i = 64; i >= 0; i--) {
                 if (i != 64) {
-                    ed_dbl(acc, false); ed_dbl(acc, false); ed_dbl(acc, false); ed_dbl(acc, true);
+                    for (int d = 0; d < 4; d++) ed_dbl<FE>(acc, d == 3);
                 }
-                ed_add_from_table(acc, tab, recode_digit<4>(kp, i), true);
+                ed_add_from_table<FE>(acc, tab, recode_digit<4>(kp, i), true);
             }
             Fe zi, ax, ay;
             fe_inv((FE*)0, zi, acc.Z);

@@ -10,6 +10,7 @@
 #pragma once
 #include "field.cuh"
 #include "consts_gen.cuh"
+#include "modinv.cuh"
 
 namespace sigops {
 
@@ -17,6 +18,7 @@ namespace sigops {
 // generic Montgomery arithmetic mod an odd 256-bit modulus, R = 2^256
 // ---------------------------------------------------------------------------------------------------------
 struct ModK1N {
+    typedef ModInvK1N MI;
     static SG_HD void mod(u32* m) {
         const u32 M[8] = SG_K1_N;
         copy8(m, M);
@@ -32,6 +34,7 @@ struct ModK1N {
     static constexpr u32 n0inv = SG_K1_N_N0INV;
 };
 struct ModR1N {
+    typedef ModInvR1N MI;
     static SG_HD void mod(u32* m) {
         const u32 M[8] = SG_R1_N;
         copy8(m, M);
@@ -103,6 +106,16 @@ struct Sc {
         reduce16(r.v, t);
         return r;
     }
+    // n successive Montgomery squarings in one out-of-line loop (squaring inlined)
+    static SG_CALL Fe msqr_n_(Fe a, int n) {
+#pragma unroll 1
+        for (int i = 0; i < n; i++) {
+            u32 t[16];
+            sqr8(t, a.v);
+            reduce16(a.v, t);
+        }
+        return a;
+    }
     static SG_HD void mmul(u32* r, const u32* a, const u32* b) {
         Fe x, y;
         copy8(x.v, a);
@@ -148,7 +161,10 @@ struct Sc {
         M::mod(m);
         return !gte8(a, m);
     }
-    // Montgomery-domain inverse by Fermat: a^(m-2), fixed 4-bit windows (256 squarings + 64 + 14 products)
+    // plain inverse a^-1 mod m for a in [0, m): safegcd
+    static SG_HD void inv_plain(u32* r, const u32* a) { ModInv<typename M::MI>::inv(r, a); }
+    // Montgomery-domain inverse by Fermat: a^(m-2), fixed 4-bit windows (256 squarings + 64 + 14 products).
+    // Kept as an independent cross-check of inv_plain in the unit tests; the kernels use inv_plain.
     static SG_HD void minv(u32* r, const u32* a) {
         u32 e[8];
         M::minus2(e);
@@ -163,10 +179,12 @@ struct Sc {
         }
 #pragma unroll 1
         for (int w = 62; w >= 0; w--) {
-            msqr(acc, acc);
-            msqr(acc, acc);
-            msqr(acc, acc);
-            msqr(acc, acc);
+            {
+                Fe x;
+                copy8(x.v, acc);
+                x = msqr_n_(x, 4);
+                copy8(acc, x.v);
+            }
             u32 d = (e[w >> 3] >> ((w & 7) * 4)) & 15u;
             if (d) mmul(acc, acc, tab[d - 1]);
         }

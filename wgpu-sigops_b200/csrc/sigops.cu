@@ -462,7 +462,7 @@ int sigops_precompute_bases(int curve, uint32_t log_limb_size, uint32_t* out, si
         FE::mul(t2d, B.T, d2);
         ed_set_identity(acc);
         for (int i = 0; i < 16; i++) {
-            ed_add_niels(acc, ypx, ymx, t2d, false, true);
+            ed_add_niels<FE>(acc, ypx, ymx, t2d, false, true);
             Fe zi, ax, ay, at;
             fe_inv((FE*)0, zi, acc.Z);
             FE::mul(ax, acc.X, zi);
