@@ -10,9 +10,25 @@
 
 using namespace sigops;
 
+// fixed-base tables, generated on the host with the same entry functions the device's gen_tables_kernel runs
+static std::vector<u32> k1_gtab, r1_gtab, ed_btab;
+static void ensure_tables() {
+    if (!k1_gtab.empty()) return;
+    k1_gtab.resize((size_t)2 * kGTabEntries * 16);
+    r1_gtab.resize((size_t)kGTabEntries * 16);
+    ed_btab.resize((size_t)kGTabEntries * 24);
+    for (u32 j = 0; j < (u32)kGTabEntries; j++) {
+        sw_gtab_entry<CurveK1>(&k1_gtab[(size_t)j * 16], j + 1, false, k1_g_host);
+        sw_gtab_entry<CurveK1>(&k1_gtab[((size_t)kGTabEntries + j) * 16], j + 1, true, k1_g_host);
+        sw_gtab_entry<CurveR1>(&r1_gtab[(size_t)j * 16], j + 1, false, r1_g_host);
+        ed_btab_entry(&ed_btab[(size_t)j * 24], j + 1, ed_b_niels_host);
+    }
+}
+
 extern "C" {
 
 int hostsim_unit(int op, const uint32_t* in, size_t n, uint32_t* out) {
+    ensure_tables();
     int in_w, out_w;
     unit_shape(op, in_w, out_w);
     std::vector<Q4> scratch(kEdTabChunks);
@@ -21,7 +37,7 @@ int hostsim_unit(int op, const uint32_t* in, size_t n, uint32_t* out) {
         u32 a[32], r[17];
         for (int j = 0; j < 32; j++) a[j] = j < in_w ? in[i * in_w + j] : 0u;
         for (int j = 0; j < 17; j++) r[j] = 0;
-        unit_dispatch(op, r, a, tab, k1_gtab, r1_gtab, ed_btab);
+        unit_dispatch(op, r, a, tab, k1_gtab.data(), r1_gtab.data(), ed_btab.data());
         for (int j = 0; j < out_w; j++) out[i * out_w + j] = r[j];
     }
     return 0;
@@ -33,14 +49,15 @@ int hostsim_unit_shape(int op, int* in_w, int* out_w) {
 }
 
 int hostsim_ecrecover(int curve, const uint8_t* sigs, const uint8_t* msgs, size_t n, uint8_t* out, uint8_t* status) {
+    ensure_tables();
     std::vector<Q4> scratch(kSwTabChunks);
     TabRef tab{scratch.data(), 1};
     for (size_t i = 0; i < n; i++) {
         u32 sig_w[16], msg_w[8], out_w[16];
         memcpy(sig_w, sigs + 64 * i, 64);
         memcpy(msg_w, msgs + 32 * i, 32);
-        u32 st = curve == 0 ? sw_ecrecover_one<CurveK1>(out_w, sig_w, msg_w, tab, k1_gtab)
-                            : sw_ecrecover_one<CurveR1>(out_w, sig_w, msg_w, tab, r1_gtab);
+        u32 st = curve == 0 ? sw_ecrecover_one<CurveK1>(out_w, sig_w, msg_w, tab, k1_gtab.data())
+                            : sw_ecrecover_one<CurveR1>(out_w, sig_w, msg_w, tab, r1_gtab.data());
         memcpy(out + 64 * i, out_w, 64);
         if (status) status[i] = (uint8_t)st;
     }
@@ -48,6 +65,7 @@ int hostsim_ecrecover(int curve, const uint8_t* sigs, const uint8_t* msgs, size_
 }
 
 int hostsim_ed25519_verify(const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n, uint8_t* valid) {
+    ensure_tables();
     std::vector<Q4> scratch(kEdTabChunks);
     TabRef tab{scratch.data(), 1};
     for (size_t i = 0; i < n; i++) {
@@ -55,7 +73,7 @@ int hostsim_ed25519_verify(const uint8_t* sigs, const uint8_t* msgs, const uint8
         memcpy(sig_w, sigs + 64 * i, 64);
         memcpy(msg_w, msgs + 32 * i, 32);
         memcpy(pk_w, pks + 32 * i, 32);
-        valid[i] = (uint8_t)ed_verify_one(sig_w, msg_w, pk_w, tab, ed_btab);
+        valid[i] = (uint8_t)ed_verify_one(sig_w, msg_w, pk_w, tab, ed_btab.data());
     }
     return 0;
 }

@@ -260,6 +260,37 @@ SG_HD void ed_add_from_btab(EdPoint& acc, const u32* btab, int d, bool need_t) {
     ed_add_niels<FE>(acc, ypx, ymx, xy2d, d < 0, need_t);
 }
 
+// Entry j (1-based) of the fixed-base table: j*B as an affine Niels triple (y+x, y-x, 2d*x*y), 24 words.
+// b_niels: the base point's own Niels triple.  Runs once per entry at init.
+SG_HD void ed_btab_entry(u32* out24, u32 j, const u32* b_niels) {
+    Fe ypx, ymx, xy2d;
+    copy8(ypx.v, b_niels);
+    copy8(ymx.v, b_niels + 8);
+    copy8(xy2d.v, b_niels + 16);
+    EdPoint P;
+    ed_set_identity(P);
+#pragma unroll 1
+    for (int b = kGWin - 1; b >= 0; b--) {
+        ed_dbl<FE>(P, true);
+        if ((j >> b) & 1u) ed_add_niels<FE>(P, ypx, ymx, xy2d, false, true);
+    }
+    const Fe d2 = {SG_ED_D2};
+    Fe zi, x, y, t;
+    fe_inv((FE*)0, zi, P.Z);
+    FE::mul(x, P.X, zi);
+    FE::mul(y, P.Y, zi);
+    FE::add(t, y, x);
+    FE::normalize(t, t);
+    copy8(out24, t.v);
+    FE::sub(t, y, x);
+    FE::normalize(t, t);
+    copy8(out24 + 8, t.v);
+    FE::mul(t, x, y);
+    FE::mul(t, t, d2);
+    FE::normalize(t, t);
+    copy8(out24 + 16, t.v);
+}
+
 // sqrt_ratio_i (curve25519-dalek; src/wgsl/ed25519_utils.wgsl:42-88): returns whether u/v is a square and the
 // nonnegative root (or of i*u/v when it is not)
 SG_HD bool ed_sqrt_ratio_i(Fe& r, const Fe& u, const Fe& v) {
@@ -355,22 +386,29 @@ SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, con
         ed_tab_store(tab, 7, T);
     }
     // R' = [s]B + [k](-A): 64 signed 4-bit windows for k, 32 signed 8-bit windows for s, 252 shared doublings
-    u32 kp[2][8];
+    u32 kp[2][10];
     copy8(kp[0], k);
     copy8(kp[1], sig_w + 8);
-    recode_add_offset<8>(kp[0], 0x88888888u, 0x88888888u);
-    recode_add_offset<8>(kp[1], 0x80808080u, 0x80808080u);
+    kp[0][8] = kp[0][9] = 0;
+    kp[1][8] = kp[1][9] = 0;
+    recode_offset<8, 4, 64>(kp[0]);      // k < L < 2^253: k + C < 2^256
+    recode_offset<9, kGWin, 22>(kp[1]);  // s < L: s + C < 2^264
     EdPoint acc;
     ed_set_identity(acc);
+    int gcount = 0;  // B windows sit on every third k window: i = 63, 60, ..., 0  <->  window i / 3
 #pragma unroll 1
     for (int i = 63; i >= 0; i--) {
         if (i != 63) {
 #pragma unroll 1
             for (int d = 0; d < 4; d++) ed_dbl<FH>(acc, d == 3);
         }
-        bool has_b = (i & 1) == 0;
         ed_add_from_table<FH>(acc, tab, recode_digit<4>(kp[0], i), true);
-        if (has_b) ed_add_from_btab<FH>(acc, btab, recode_digit<8>(kp[1], i >> 1), true);
+        if (gcount == 0) {
+            ed_add_from_btab<FH>(acc, btab, recode_digit<kGWin>(kp[1], (i * 43) >> 7 /* i / 3 */), true);
+            gcount = 2;
+        } else {
+            gcount--;
+        }
     }
     // compress and compare with the signature's R bytes
     Fe zi, ax, ay;

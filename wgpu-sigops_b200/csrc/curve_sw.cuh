@@ -247,46 +247,95 @@ SG_HD void jac_add(JacPoint& P, const Fe& X2, const Fe& Y2, const Fe& Z2) {
     jac_add_tail<F>(P, U1, S1, H, r, Zm);
 }
 
-// table entry e (0-based: (e+1)*R) occupies chunks [6e, 6e+6): X, Y, Z
-SG_HD void tab_store_jac(const TabRef& t, int e, const JacPoint& P) {
-    tab_store_fe(t, 6 * e + 0, P.X);
-    tab_store_fe(t, 6 * e + 2, P.Y);
-    tab_store_fe(t, 6 * e + 4, P.Z);
-}
+// ---------------------------------------------------------------------------------------------------------
+// Per-signature table {1..8} * R in AFFINE coordinates (signed 4-bit windows).  Built as Jacobian points, then
+// normalised with ONE shared inversion (Montgomery's trick; the inversion itself is the cheap safegcd one), so every
+// addition in the main loop is a mixed addition (8M + 3S instead of 12M + 4S): 66 additions x 5 products saved for
+// ~70 products of conversion work per signature on secp256k1.
+// Scratch layout in 16-byte chunks: entry e (0-based, (e+1)*R): x at 4e, y at 4e+2  (32 chunks);
+//   Z_j (j = 2..8) at 32 + 2(j-2);  prefix products c_j = Z_2...Z_j at 46 + 2(j-2)   -> 60 chunks (960 B) per thread.
+// ---------------------------------------------------------------------------------------------------------
+static constexpr int kSwTabEntries = 8;
+static constexpr int kSwTabChunks = 60;
+static constexpr int kSwTabZ = 32, kSwTabC = 46;
 
-static constexpr int kSwTabEntries = 8;                      // {1..8} * R, signed 4-bit windows
-static constexpr int kSwTabChunks = kSwTabEntries * 6;       // 16-byte chunks per thread (768 B)
+// fixed-base tables: j*G for j = 1..2^(kGWin-1), affine (x, y) in the field's internal form, 16 words per entry;
+// secp256k1 carries a second table for lambda*G = (beta*x, y) right behind the first one.  Generated once per device at
+// init (gen_tables_kernel); 12-bit signed windows: 11 additions per 128-bit half scalar, 22 per 256-bit scalar.
+static constexpr int kGWin = 12;
+static constexpr int kGTabEntries = 1 << (kGWin - 1);
 
-// Build {1..8}*R from affine R = (x, y): 4 doublings + 3 mixed additions
 template <class C>
 SG_HD void sw_build_table(const TabRef& tab, const Fe& x, const Fe& y) {
     typedef typename C::F F;
-    JacPoint P1, P2, P3, P4, T;
-    P1.X = x;
-    P1.Y = y;
-    F::set_one(P1.Z);
-    P1.inf = false;
-    tab_store_jac(tab, 0, P1);
-    P2 = P1;
-    jac_dbl<C>(P2);
-    tab_store_jac(tab, 1, P2);
-    P3 = P2;
-    jac_madd<C>(P3, x, y);
-    tab_store_jac(tab, 2, P3);
-    P4 = P2;
-    jac_dbl<C>(P4);
-    tab_store_jac(tab, 3, P4);
-    T = P4;
-    jac_madd<C>(T, x, y);
-    tab_store_jac(tab, 4, T);  // 5R
-    T = P3;
-    jac_dbl<C>(T);
-    tab_store_jac(tab, 5, T);  // 6R
-    jac_madd<C>(T, x, y);
-    tab_store_jac(tab, 6, T);  // 7R
-    T = P4;
-    jac_dbl<C>(T);
-    tab_store_jac(tab, 7, T);  // 8R
+    tab_store_fe(tab, 0, x);
+    tab_store_fe(tab, 2, y);
+    // Jacobian multiples 2R..8R: X, Y parked in their final slots, Z in the temp area
+    {
+        JacPoint P1, P2, P3, P4, T;
+        P1.X = x;
+        P1.Y = y;
+        F::set_one(P1.Z);
+        P1.inf = false;
+        P2 = P1;
+        jac_dbl<C>(P2);
+        P3 = P2;
+        jac_madd<C>(P3, x, y);
+        P4 = P2;
+        jac_dbl<C>(P4);
+#define SG_PARK(e, P)                           \
+    tab_store_fe(tab, 4 * (e), (P).X);          \
+    tab_store_fe(tab, 4 * (e) + 2, (P).Y);      \
+    tab_store_fe(tab, kSwTabZ + 2 * ((e)-1), (P).Z)
+        SG_PARK(1, P2);
+        SG_PARK(2, P3);
+        SG_PARK(3, P4);
+        T = P4;
+        jac_madd<C>(T, x, y);
+        SG_PARK(4, T);  // 5R
+        T = P3;
+        jac_dbl<C>(T);
+        SG_PARK(5, T);  // 6R
+        jac_madd<C>(T, x, y);
+        SG_PARK(6, T);  // 7R
+        T = P4;
+        jac_dbl<C>(T);
+        SG_PARK(7, T);  // 8R
+#undef SG_PARK
+    }
+    // prefix products c_j = Z_2 * ... * Z_j  (R has prime order n > 8: no multiple is infinity, every Z_j != 0)
+    Fe c, z;
+    tab_load_fe(c, tab, kSwTabZ);
+    tab_store_fe(tab, kSwTabC, c);
+#pragma unroll 1
+    for (int j = 3; j <= 8; j++) {
+        tab_load_fe(z, tab, kSwTabZ + 2 * (j - 2));
+        F::mul(c, c, z);
+        tab_store_fe(tab, kSwTabC + 2 * (j - 2), c);
+    }
+    Fe inv;
+    fe_inv((F*)0, inv, c);
+    // walk back: zinv_j = inv * c_(j-1), inv <- inv * Z_j; then x = X / Z^2, y = Y / Z^3
+#pragma unroll 1
+    for (int j = 8; j >= 2; j--) {
+        Fe zi, zi2, t;
+        if (j > 2) {
+            tab_load_fe(t, tab, kSwTabC + 2 * (j - 3));
+            F::mul(zi, inv, t);
+            tab_load_fe(z, tab, kSwTabZ + 2 * (j - 2));
+            F::mul(inv, inv, z);
+        } else {
+            zi = inv;
+        }
+        F::sqr(zi2, zi);
+        tab_load_fe(t, tab, 4 * (j - 1));
+        F::mul(t, t, zi2);
+        tab_store_fe(tab, 4 * (j - 1), t);
+        F::mul(zi2, zi2, zi);
+        tab_load_fe(t, tab, 4 * (j - 1) + 2);
+        F::mul(t, t, zi2);
+        tab_store_fe(tab, 4 * (j - 1) + 2, t);
+    }
 }
 
 // acc += sign(d) * |d| * R (optionally mapped through the endomorphism (x,y) -> (beta*x, y))
@@ -295,18 +344,17 @@ SG_HD void sw_add_from_table(JacPoint& acc, const TabRef& tab, int d, bool flip,
     typedef typename C::F F;
     if (d == 0) return;
     int e = (d < 0 ? -d : d) - 1;
-    Fe X, Y, Z;
-    tab_load_fe(X, tab, 6 * e + 0);
-    tab_load_fe(Y, tab, 6 * e + 2);
-    tab_load_fe(Z, tab, 6 * e + 4);
-    if ((d < 0) != flip) F::neg(Y, Y);
-    if (C::kGlv && endo) C::mul_beta(X, X);
-    jac_add<C>(acc, X, Y, Z);
+    Fe x, y;
+    tab_load_fe(x, tab, 4 * e + 0);
+    tab_load_fe(y, tab, 4 * e + 2);
+    if ((d < 0) != flip) F::neg(y, y);
+    if (C::kGlv && endo) C::mul_beta(x, x);
+    jac_madd<C>(acc, x, y);
 }
 
-// acc += sign(d) * |d| * G from the shared affine table (entry j-1 = j*G: x at words [16(j-1), +8), y next)
+// acc += sign(d) * |d| * G from a fixed-base table in global memory (entry j-1 = j*G: x at words [16(j-1), +8), y next)
 template <class C>
-SG_HD void sw_add_from_gtab(JacPoint& acc, const u32* gtab, int d, bool flip, bool endo) {
+SG_HD void sw_add_from_gtab(JacPoint& acc, const u32* gtab, int d, bool flip) {
     typedef typename C::F F;
     if (d == 0) return;
     int e = (d < 0 ? -d : d) - 1;
@@ -318,16 +366,46 @@ SG_HD void sw_add_from_gtab(JacPoint& acc, const u32* gtab, int d, bool flip, bo
     y.v[0] = c.x; y.v[1] = c.y; y.v[2] = c.z; y.v[3] = c.w;
     y.v[4] = dd.x; y.v[5] = dd.y; y.v[6] = dd.z; y.v[7] = dd.w;
     if ((d < 0) != flip) F::neg(y, y);
-    if (C::kGlv && endo) C::mul_beta(x, x);
     jac_madd<C>(acc, x, y);
 }
 
-// Q = u1*G + u2*R.  secp256k1: u1, u2 are GLV-split into four <=128-bit streams, 33 signed 4-bit windows for the
-// R streams and 17 signed 8-bit windows for the G streams share 128 doublings.  secp256r1: two 256-bit streams,
-// 65 / 33 windows over 256 doublings.
+// Entry j (1-based multiple) of a fixed-base table: j*G (or lambda*j*G) as affine x || y in the internal form.
+// g_xy: the generator in internal form (16 words).  Runs once per entry at init (device) or at load (host simulation).
+template <class C>
+SG_HD void sw_gtab_entry(u32* out16, u32 j, bool endo, const u32* g_xy) {
+    typedef typename C::F F;
+    Fe gx, gy;
+    F::from_table(gx, g_xy);
+    F::from_table(gy, g_xy + 8);
+    JacPoint P;
+    P.inf = true;
+    F::set_zero(P.X);
+    F::set_zero(P.Y);
+    F::set_zero(P.Z);
+#pragma unroll 1
+    for (int b = kGWin - 1; b >= 0; b--) {
+        jac_dbl<C>(P);
+        if ((j >> b) & 1u) jac_madd<C>(P, gx, gy);
+    }
+    Fe zi, zi2, ax, ay;
+    fe_inv((F*)0, zi, P.Z);
+    F::sqr(zi2, zi);
+    F::mul(ax, P.X, zi2);
+    F::mul(zi2, zi2, zi);
+    F::mul(ay, P.Y, zi2);
+    if (C::kGlv && endo) C::mul_beta(ax, ax);
+    F::normalize(ax, ax);
+    F::normalize(ay, ay);
+    copy8(out16, ax.v);
+    copy8(out16 + 8, ay.v);
+}
+
+// Q = u1*G + u2*R.  secp256k1: u1, u2 are GLV-split into four <=128-bit streams; 33 signed 4-bit windows for the two
+// R streams and 11 signed 12-bit windows for the two G streams share 128 doublings.  secp256r1: two 256-bit streams,
+// 65 / 22 windows over 256 doublings.
 template <class C>
 SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabRef& tab, const u32* gtab) {
-    typedef typename C::Hot H;  // products inlined: exactly one doubling, one addition, one mixed-addition site
+    typedef typename C::Hot H;
     acc.inf = true;
     C::F::set_zero(acc.X);
     C::F::set_zero(acc.Y);
@@ -336,7 +414,7 @@ SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabR
         GlvSplit sr, sg;
         k1_glv_split(sr, u2);
         k1_glv_split(sg, u1);
-        u32 kp[4][5];
+        u32 kp[4][6];
 #pragma unroll
         for (int i = 0; i < 5; i++) {
             kp[0][i] = sr.k1[i];
@@ -344,11 +422,14 @@ SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabR
             kp[2][i] = sg.k1[i];
             kp[3][i] = sg.k2[i];
         }
-        recode_add_offset<5>(kp[0], 0x88888888u, 0x8u);
-        recode_add_offset<5>(kp[1], 0x88888888u, 0x8u);
-        recode_add_offset<5>(kp[2], 0x80808080u, 0x80u);
-        recode_add_offset<5>(kp[3], 0x80808080u, 0x80u);
+#pragma unroll
+        for (int s = 0; s < 4; s++) kp[s][5] = 0;
+        recode_offset<5, 4, 33>(kp[0]);
+        recode_offset<5, 4, 33>(kp[1]);
+        recode_offset<5, kGWin, 11>(kp[2]);
+        recode_offset<5, kGWin, 11>(kp[3]);
         const bool flip[4] = {sr.neg1, sr.neg2, sg.neg1, sg.neg2};
+        int gcount = 0;  // i % 3 without a division: G windows sit on every third R window
 #pragma unroll 1
         for (int i = 32; i >= 0; i--) {
             if (i != 32) {
@@ -357,23 +438,31 @@ SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabR
             }
 #pragma unroll 1
             for (int s = 0; s < 2; s++) sw_add_from_table<H>(acc, tab, recode_digit<4>(kp[s], i), flip[s], s == 1);
-            if ((i & 1) == 0) {
+            // i = 30, 27, ..., 0  <->  G window i / 3 = 10 ... 0   (i = 32, 31 carry no G window)
+            if (i <= 30) {
+                if (gcount == 0) {
 #pragma unroll 1
-                for (int s = 2; s < 4; s++)
-                    sw_add_from_gtab<H>(acc, gtab, recode_digit<8>(kp[s], i >> 1), flip[s], s == 3);
+                    for (int s = 2; s < 4; s++)
+                        sw_add_from_gtab<H>(acc, gtab + (s == 3 ? kGTabEntries * 16 : 0),
+                                            recode_digit<kGWin>(kp[s], (i * 11) >> 5 /* i / 3 for i <= 30 */), flip[s]);
+                    gcount = 2;
+                } else {
+                    gcount--;
+                }
             }
         }
     } else {
-        u32 kp[2][9];
+        u32 kp[2][10];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             kp[0][i] = u2[i];
             kp[1][i] = u1[i];
         }
-        kp[0][8] = 0;
-        kp[1][8] = 0;
-        recode_add_offset<9>(kp[0], 0x88888888u, 0x8u);
-        recode_add_offset<9>(kp[1], 0x80808080u, 0x80u);
+        kp[0][8] = kp[0][9] = 0;
+        kp[1][8] = kp[1][9] = 0;
+        recode_offset<9, 4, 65>(kp[0]);
+        recode_offset<9, kGWin, 22>(kp[1]);
+        int gcount = 0;
 #pragma unroll 1
         for (int i = 64; i >= 0; i--) {
             if (i != 64) {
@@ -381,7 +470,15 @@ SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabR
                 for (int d = 0; d < 4; d++) jac_dbl<H>(acc);
             }
             sw_add_from_table<H>(acc, tab, recode_digit<4>(kp[0], i), false, false);
-            if ((i & 1) == 0) sw_add_from_gtab<H>(acc, gtab, recode_digit<8>(kp[1], i >> 1), false, false);
+            // i = 63, 60, ..., 0  <->  G window i / 3 = 21 ... 0
+            if (i <= 63) {
+                if (gcount == 0) {
+                    sw_add_from_gtab<H>(acc, gtab, recode_digit<kGWin>(kp[1], (i * 43) >> 7 /* i / 3 for i < 128 */), false);
+                    gcount = 2;
+                } else {
+                    gcount--;
+                }
+            }
         }
     }
 }

@@ -28,20 +28,10 @@ static constexpr int kBlock = SG_BLOCK;
 
 #if defined(__CUDACC__)
 
-// Copy a constant table into shared memory (generator table staged per block)
-__device__ __forceinline__ void stage_table(u32* dst, const u32* src, int words) {
-    const Q4* s = reinterpret_cast<const Q4*>(src);
-    Q4* d = reinterpret_cast<Q4*>(dst);
-    for (int i = threadIdx.x; i < words / 4; i += blockDim.x) d[i] = s[i];
-    __syncthreads();
-}
-
 template <class C>
 __global__ void __launch_bounds__(kBlock, SG_MINB_SW) ecrecover_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
                                                            size_t n, Q4* __restrict__ out, uint8_t* __restrict__ status,
-                                                           Q4* __restrict__ scratch, const u32* __restrict__ gtab_g) {
-    __shared__ __align__(16) u32 gtab[SG_GTAB_ENTRIES * 16];
-    stage_table(gtab, gtab_g, SG_GTAB_ENTRIES * 16);
+                                                           Q4* __restrict__ scratch, const u32* __restrict__ gtab) {
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     TabRef tab;
@@ -78,9 +68,7 @@ __global__ void __launch_bounds__(kBlock, SG_MINB_SW) ecrecover_kernel(const Q4*
 __global__ void __launch_bounds__(kBlock, SG_MINB_ED) ed25519_verify_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
                                                                 const Q4* __restrict__ pks, size_t n,
                                                                 uint8_t* __restrict__ valid, Q4* __restrict__ scratch,
-                                                                const u32* __restrict__ btab_g) {
-    __shared__ __align__(16) u32 btab[SG_GTAB_ENTRIES * 24];
-    stage_table(btab, btab_g, SG_GTAB_ENTRIES * 24);
+                                                                const u32* __restrict__ btab) {
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     TabRef tab;
@@ -111,6 +99,25 @@ __global__ void __launch_bounds__(kBlock, SG_MINB_ED) ed25519_verify_kernel(cons
         }
         valid[i] = (uint8_t)ed_verify_one(sig_w, msg_w, pk_w, tab, btab);
     }
+}
+
+// Fixed-base tables, generated once per device at init: thread j writes entry j (the (j+1)-th multiple) of
+//   k1tab  [2][kGTabEntries][16]  j*G and lambda*j*G        r1tab [kGTabEntries][16]  j*G (Montgomery form)
+//   edtab  [kGTabEntries][24]     j*B as affine Niels triples
+// from the baked single generators (consts_gen.cuh).  Replaces the 16-entry tables of src/precompute.rs:14-69 that the
+// reference uploads on every call (src/secp256k1_ecdsa.rs:108).
+__global__ void __launch_bounds__(64) gen_tables_kernel(u32* k1tab, u32* r1tab, u32* edtab) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (u32)kGTabEntries) return;
+    u32 e[24];
+    sw_gtab_entry<CurveK1>(e, j + 1, false, k1_g_dev);
+    for (int i = 0; i < 16; i++) k1tab[(size_t)j * 16 + i] = e[i];
+    sw_gtab_entry<CurveK1>(e, j + 1, true, k1_g_dev);
+    for (int i = 0; i < 16; i++) k1tab[((size_t)kGTabEntries + j) * 16 + i] = e[i];
+    sw_gtab_entry<CurveR1>(e, j + 1, false, r1_g_dev);
+    for (int i = 0; i < 16; i++) r1tab[(size_t)j * 16 + i] = e[i];
+    ed_btab_entry(e, j + 1, ed_b_niels_dev);
+    for (int i = 0; i < 24; i++) edtab[(size_t)j * 24 + i] = e[i];
 }
 
 #endif  // __CUDACC__
@@ -347,7 +354,7 @@ SG_HD void unit_dispatch(int op, u32* out, const u32* in, const TabRef& tab, con
             u32 kp[9];
             for (int i = 0; i < 8; i++) kp[i] = in[i];
             kp[8] = 0;
-            recode_add_offset<9>(kp, 0x88888888u, 0x8u);
+            recode_offset<9, 4, 65>(kp);
             ed_set_identity(acc);
             for (int i = 64; i >= 0; i--) {
                 if (i != 64) {

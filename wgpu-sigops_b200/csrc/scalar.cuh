@@ -250,25 +250,34 @@ SG_HD void k1_glv_split(GlvSplit& out, const u32* k) {
 // d_i = u_i - 2^(W-1) in [-2^(W-1), 2^(W-1)) with k = sum d_i 2^(W*i)   (requires k + C < 2^(W*NW)).
 // Every lane adds at the same iterations -> no divergence except on d_i == 0.
 // ---------------------------------------------------------------------------------------------------------
-template <int NLIMBS>
-SG_HD void recode_add_offset(u32* k, u32 pattern, u32 top_pattern) {
-    // k += pattern in limbs 0..NLIMBS-2 and top_pattern in the last limb
-    // (W=4: 0x88888888 / 0x8 or 0x88888888;  W=8: 0x80808080 / 0x80 or 0x80808080)
+// k (NL limbs) += sum_{i < NW} 2^(W-1) * 2^(W*i): the offset that turns unsigned W-bit windows into signed digits.
+// The per-limb pattern is a compile-time constant after unrolling.
+template <int NL, int W, int NW>
+SG_HD void recode_offset(u32* k) {
     u64 c = 0;
 #pragma unroll
-    for (int i = 0; i < NLIMBS; i++) {
-        c += (u64)k[i] + (i == NLIMBS - 1 ? top_pattern : pattern);
-        k[i] = (u32)c;
+    for (int l = 0; l < NL; l++) {
+        u32 pat = 0;
+#pragma unroll
+        for (int i = 0; i < NW; i++) {
+            const int bit = W * i + W - 1;
+            if ((bit >> 5) == l) pat |= 1u << (bit & 31);
+        }
+        c += (u64)k[l] + pat;
+        k[l] = (u32)c;
         c >>= 32;
     }
 }
 
-// signed digit of window i (width W) of the offset scalar k'
+// signed digit of window i (width W) of the offset scalar k'; windows may straddle limbs (the array must extend one
+// limb past the last window's low limb)
 template <int W>
 SG_HD int recode_digit(const u32* kp, int i) {
-    const int per = 32 / W;
-    u32 u = (kp[i / per] >> ((i % per) * W)) & ((1u << W) - 1u);
-    return (int)u - (1 << (W - 1));
+    const int bit = W * i;
+    const int w = bit >> 5, sh = bit & 31;
+    u32 v = kp[w] >> sh;
+    if (sh + W > 32) v |= kp[w + 1] << (32 - sh);
+    return (int)(v & ((1u << W) - 1u)) - (1 << (W - 1));
 }
 
 }  // namespace sigops

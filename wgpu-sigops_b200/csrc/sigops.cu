@@ -107,13 +107,18 @@ int init_device(Device& d, int id) {
     d.sms = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
     for (auto& e : d.ev) CK(cudaEventCreate(&e));
-    void* p = nullptr;
-    CK(cudaGetSymbolAddress(&p, k1_gtab));
-    d.k1g = (const u32*)p;
-    CK(cudaGetSymbolAddress(&p, r1_gtab));
-    d.r1g = (const u32*)p;
-    CK(cudaGetSymbolAddress(&p, ed_btab));
-    d.edb = (const u32*)p;
+    // fixed-base tables: computed on the device once, resident for the life of the context (L2-sized: 576 KB)
+    u32 *k1t = nullptr, *r1t = nullptr, *edt = nullptr;
+    CK(cudaMalloc((void**)&k1t, (size_t)2 * kGTabEntries * 16 * sizeof(u32)));
+    CK(cudaMalloc((void**)&r1t, (size_t)kGTabEntries * 16 * sizeof(u32)));
+    CK(cudaMalloc((void**)&edt, (size_t)kGTabEntries * 24 * sizeof(u32)));
+    gen_tables_kernel<<<(kGTabEntries + 63) / 64, 64, 0, d.stream>>>(k1t, r1t, edt);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(d.stream));
+    g_launches++;
+    d.k1g = k1t;
+    d.r1g = r1t;
+    d.edb = edt;
     if (max_grid(d, ecrecover_kernel<CurveK1>, &d.grid_k1)) return 1;
     if (max_grid(d, ecrecover_kernel<CurveR1>, &d.grid_r1)) return 1;
     if (max_grid(d, ed25519_verify_kernel, &d.grid_ed)) return 1;
@@ -349,6 +354,9 @@ int sigops_shutdown(void) {
         if (d.d_in) cudaFree(d.d_in);
         if (d.d_out) cudaFree(d.d_out);
         if (d.scratch) cudaFree(d.scratch);
+        if (d.k1g) cudaFree((void*)d.k1g);
+        if (d.r1g) cudaFree((void*)d.r1g);
+        if (d.edb) cudaFree((void*)d.edb);
         for (auto& e : d.ev)
             if (e) cudaEventDestroy(e);
         if (d.stream) cudaStreamDestroy(d.stream);
