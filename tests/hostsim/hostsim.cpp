@@ -56,8 +56,8 @@ int hostsim_ecrecover(int curve, const uint8_t* sigs, const uint8_t* msgs, size_
         u32 sig_w[16], msg_w[8], out_w[16];
         memcpy(sig_w, sigs + 64 * i, 64);
         memcpy(msg_w, msgs + 32 * i, 32);
-        u32 st = curve == 0 ? sw_ecrecover_one<CurveK1>(out_w, sig_w, msg_w, tab, k1_gtab.data())
-                            : sw_ecrecover_one<CurveR1>(out_w, sig_w, msg_w, tab, r1_gtab.data());
+        u32 st = curve == 0 ? sw_ecrecover_one<CurveK1, false>(out_w, sig_w, msg_w, tab, k1_gtab.data())
+                            : sw_ecrecover_one<CurveR1, false>(out_w, sig_w, msg_w, tab, r1_gtab.data());
         memcpy(out + 64 * i, out_w, 64);
         if (status) status[i] = (uint8_t)st;
     }
@@ -73,7 +73,7 @@ int hostsim_ed25519_verify(const uint8_t* sigs, const uint8_t* msgs, const uint8
         memcpy(sig_w, sigs + 64 * i, 64);
         memcpy(msg_w, msgs + 32 * i, 32);
         memcpy(pk_w, pks + 32 * i, 32);
-        valid[i] = (uint8_t)ed_verify_one(sig_w, msg_w, pk_w, tab, ed_btab.data());
+        valid[i] = (uint8_t)ed_verify_one<false>(sig_w, msg_w, pk_w, tab, ed_btab.data());
     }
     return 0;
 }

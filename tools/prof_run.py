@@ -3,6 +3,7 @@
    python tools/prof_run.py [n] [reps] [curves]"""
 import os
 import sys
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
@@ -32,17 +33,23 @@ def main():
     for c in curves:
         if c == "ed25519":
             s, m, p = coracle.gen_ed25519(pool)
+            ts, tm, tp = tile(s), tile(m), tile(p)
             for _ in range(reps):
-                v = w.ed25519_eddsa.ecverify_array(tile(s), tile(m), tile(p))
+                t0 = time.perf_counter()
+                v = w.ed25519_eddsa.ecverify_array(ts, tm, tp)
+                wall = time.perf_counter() - t0
             assert v.all()
         else:
             cid = 0 if c == "secp256k1" else 1
             s, m, e = coracle.gen_ecdsa(cid, pool)
             mod = w.secp256k1_ecdsa if cid == 0 else w.secp256r1_ecdsa
+            ts, tm = tile(s), tile(m)
             for _ in range(reps):
-                out, st = mod.ecrecover_with_status(tile(s), tile(m))
+                t0 = time.perf_counter()
+                out, st = mod.ecrecover_with_status(ts, tm)
+                wall = time.perf_counter() - t0
             assert (out == tile(e)).all() and not st.any()
-        print(c, "ok", ("%.3f ms %.2f Msig/s" % (ktime(), n / ktime() / 1e3)) if timing else "", flush=True)
+        print(c, "ok", ("%.3f ms %.2f Msig/s kernel span; wall %.2f Msig/s (pageable host buffers)" % (ktime(), n / ktime() / 1e3, n / wall / 1e6)) if timing else "", flush=True)
 
 
 if __name__ == "__main__":

@@ -39,7 +39,7 @@ def run(n):
     for f in sorted(os.listdir(VDIR)):
         if not f.endswith(".so"):
             continue
-        env = dict(os.environ, SIGOPS_LIB=os.path.join(VDIR, f))
+        env = dict(os.environ, SIGOPS_LIB=os.path.join(VDIR, f), SIGOPS_MAX_CHUNKS=os.environ.get("SIGOPS_MAX_CHUNKS", "1"))
         p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "prof_run.py"), str(n), "3", "time"], env=env,
                            capture_output=True, text=True, timeout=600)
         print("==", f, p.stdout.strip().replace("\n", " | "), p.stderr[-300:] if p.returncode else "", flush=True)

@@ -318,6 +318,7 @@ SG_HD bool ed_sqrt_ratio_i(Fe& r, const Fe& u, const Fe& v) {
 
 // One signature: sig_w 16 words (R || s), msg_w 8 words, pk_w 8 words (all little-endian-loaded bytes).
 // Returns 1 when the signature verifies, else 0.
+template <bool kSync>
 SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, const TabRef& tab, const u32* btab) {
     typedef Sc<ModEdL> S;
 #if defined(SG_HOT_INLINE)
@@ -336,11 +337,15 @@ SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, con
     FE::sub(u, yy, one);
     FE::mul(v, yy, dconst);
     FE::add(v, v, one);
-    if (!ed_sqrt_ratio_i(x, u, v)) return 0;
+    phase_sync<kSync>();
+    // No early exit (every thread of the block must reach every phase barrier): a key that does not decompress or a
+    // non-canonical s keeps walking the program on whatever values it has and the verdict is forced to 0 at the end.
+    bool ok = ed_sqrt_ratio_i(x, u, v);
     // -A: negate x exactly when the sign bit is clear (x from sqrt_ratio_i is the nonnegative root)
     if (!sign) FE::neg(x, x);
     // canonical-scalar check on s
-    if (!S::lt_mod(sig_w + 8)) return 0;
+    ok = ok && S::lt_mod(sig_w + 8);
+    phase_sync<kSync>();
     // k = SHA-512(R || A || M) mod L
     u32 pre[24], dig[16], k[8];
 #pragma unroll
@@ -352,6 +357,7 @@ SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, con
     sha512_96(dig, pre);
     ed_reduce512(k, dig);
     // table {1..8} * (-A), cached form
+    phase_sync<kSync>();
     {
         EdPoint P1, P2, P3, P4, T;
         P1.X = x;
@@ -398,6 +404,7 @@ SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, con
     int gcount = 0;  // B windows sit on every third k window: i = 63, 60, ..., 0  <->  window i / 3
 #pragma unroll 1
     for (int i = 63; i >= 0; i--) {
+        phase_sync<kSync>();
         if (i != 63) {
 #pragma unroll 1
             for (int d = 0; d < 4; d++) ed_dbl<FH>(acc, d == 3);
@@ -411,6 +418,7 @@ SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, con
         }
     }
     // compress and compare with the signature's R bytes
+    phase_sync<kSync>();
     Fe zi, ax, ay;
     fe_inv((FE*)0, zi, acc.Z);
     FE::mul(ax, acc.X, zi);
@@ -418,7 +426,7 @@ SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, con
     u32 enc[8];
     FE::to_plain(enc, ay);
     enc[7] |= (FE::is_negative(ax) ? 1u : 0u) << 31;
-    return eq8(enc, sig_w) ? 1u : 0u;
+    return (ok && eq8(enc, sig_w)) ? 1u : 0u;
 }
 
 }  // namespace sigops

@@ -13,17 +13,26 @@
 namespace sigops {
 
 #ifndef SG_BLOCK
-#define SG_BLOCK 64
+#define SG_BLOCK 512
 #endif
 static constexpr int kBlock = SG_BLOCK;
-// minimum resident blocks per SM the register allocation must allow (occupancy knob).
-// Measured on B200 (profiles/r01_variants.md): 64-thread blocks x 7 (<= 128 registers, 14-16 warps/SM) beat the
-// unconstrained build (188-250 registers, 8 warps/SM) by 10-14% despite ~1 KB of spills per thread.
+// Launch bounds: 512 threads x 1 block per SM => at most 128 registers per thread, 16 warps per SM.  Measured on B200
+// (profiles/r01_variants.md): 14-16 warps/SM beat the unconstrained build (188-250 registers, 8 warps/SM) by 10-14%
+// despite ~1 KB of spills per thread, and ONE block per SM with a barrier per phase of the per-signature program beats
+// seven independent 64-thread blocks by another 12-27% (instruction-cache locality).
 #ifndef SG_MINB_SW
-#define SG_MINB_SW 7
+#define SG_MINB_SW 1
 #endif
 #ifndef SG_MINB_ED
-#define SG_MINB_ED 7
+#define SG_MINB_ED 1
+#endif
+
+// Barriers inside the per-signature program (between its phases and per window of the main loop) on top of the one per
+// signature: measured 2-4% slower than the per-signature barrier alone, so off by default.
+#if defined(SG_INNER_SYNC)
+static constexpr bool kInnerSync = true;
+#else
+static constexpr bool kInnerSync = false;
 #endif
 
 #if defined(__CUDACC__)
@@ -37,7 +46,13 @@ __global__ void __launch_bounds__(kBlock, SG_MINB_SW) ecrecover_kernel(const Q4*
     TabRef tab;
     tab.base = scratch + gid;
     tab.stride = (u32)nthreads;
-    for (size_t i = gid; i < n; i += nthreads) {
+    // Uniform trip count per block: lanes past the end redo the last signature and drop the result, so that every thread
+    // reaches every phase barrier.
+    for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += nthreads) {
+        phase_sync<true>();
+        size_t i = base + threadIdx.x;
+        const bool live = i < n;
+        if (!live) i = n - 1;
         u32 sig_w[16], msg_w[8], out_w[16];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -55,13 +70,15 @@ __global__ void __launch_bounds__(kBlock, SG_MINB_SW) ecrecover_kernel(const Q4*
             msg_w[4 * q + 2] = v.z;
             msg_w[4 * q + 3] = v.w;
         }
-        u32 st = sw_ecrecover_one<C>(out_w, sig_w, msg_w, tab, gtab);
+        u32 st = sw_ecrecover_one<C, kInnerSync>(out_w, sig_w, msg_w, tab, gtab);
+        if (live) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            Q4 v = {out_w[4 * q + 0], out_w[4 * q + 1], out_w[4 * q + 2], out_w[4 * q + 3]};
-            out[4 * i + q] = v;
+            for (int q = 0; q < 4; q++) {
+                Q4 v = {out_w[4 * q + 0], out_w[4 * q + 1], out_w[4 * q + 2], out_w[4 * q + 3]};
+                out[4 * i + q] = v;
+            }
+            if (status) status[i] = (uint8_t)st;
         }
-        if (status) status[i] = (uint8_t)st;
     }
 }
 
@@ -74,7 +91,11 @@ __global__ void __launch_bounds__(kBlock, SG_MINB_ED) ed25519_verify_kernel(cons
     TabRef tab;
     tab.base = scratch + gid;
     tab.stride = (u32)nthreads;
-    for (size_t i = gid; i < n; i += nthreads) {
+    for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += nthreads) {
+        phase_sync<true>();
+        size_t i = base + threadIdx.x;
+        const bool live = i < n;
+        if (!live) i = n - 1;
         u32 sig_w[16], msg_w[8], pk_w[8];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -97,7 +118,8 @@ __global__ void __launch_bounds__(kBlock, SG_MINB_ED) ed25519_verify_kernel(cons
             pk_w[4 * q + 2] = p.z;
             pk_w[4 * q + 3] = p.w;
         }
-        valid[i] = (uint8_t)ed_verify_one(sig_w, msg_w, pk_w, tab, btab);
+        const u32 v = ed_verify_one<kInnerSync>(sig_w, msg_w, pk_w, tab, btab);
+        if (live) valid[i] = (uint8_t)v;
     }
 }
 
@@ -193,7 +215,7 @@ SG_HD void unit_double_mul(u32* out, const u32* u1, const u32* u2, const u32* xy
     F::from_plain(y, xy + 8);
     sw_build_table<C>(tab, x, y);
     JacPoint Q;
-    sw_double_mul<C>(Q, u1, u2, tab, gtab);
+    sw_double_mul<C, false>(Q, u1, u2, tab, gtab);
     for (int i = 0; i < 17; i++) out[i] = 0;
     if (Q.inf) {
         out[16] = 1;

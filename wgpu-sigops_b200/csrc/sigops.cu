@@ -45,8 +45,9 @@ void set_err(const std::string& s) { g_err = s; }
 struct Device {
     int id = -1;
     int sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;  // kernels / uploads / downloads
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_in[8] = {}, ev_k[8] = {};
     // device buffers (grow-only)
     uint8_t* d_in = nullptr;
     size_t in_cap = 0;
@@ -106,7 +107,11 @@ int init_device(Device& d, int id) {
     }
     d.sms = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&d.s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&d.s_out, cudaStreamNonBlocking));
     for (auto& e : d.ev) CK(cudaEventCreate(&e));
+    for (auto& e : d.ev_in) CK(cudaEventCreateWithFlags(&e, cudaEventDefault));
+    for (auto& e : d.ev_k) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     // fixed-base tables: computed on the device once, resident for the life of the context (L2-sized: 576 KB)
     u32 *k1t = nullptr, *r1t = nullptr, *edt = nullptr;
     CK(cudaMalloc((void**)&k1t, (size_t)2 * kGTabEntries * 16 * sizeof(u32)));
@@ -177,22 +182,30 @@ int launch_op(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_msgs, co
               uint8_t* d_out, uint8_t* d_status, cudaStream_t st) {
     if (n == 0) return 0;
     int max_g = op == OP_K1 ? d.grid_k1 : op == OP_R1 ? d.grid_r1 : d.grid_ed;
-    size_t blocks = (n + kBlock - 1) / kBlock;
+    // Geometry: full 512-thread blocks (one per SM, all 16 warps phase-locked by the kernels' barriers) once the batch
+    // covers the device; smaller batches are spread over all SMs with proportionally smaller blocks instead of filling
+    // a few SMs to the brim (latency of the 64 ... 64k end of the batch-size sweep).
+    int tpb = kBlock;
+    if (n < (size_t)d.sms * kBlock) {
+        size_t per_sm = (n + d.sms - 1) / d.sms;
+        tpb = (int)std::min<size_t>(kBlock, std::max<size_t>(32, (per_sm + 31) / 32 * 32));
+    }
+    size_t blocks = (n + tpb - 1) / tpb;
     int grid = (int)std::min<size_t>(blocks, (size_t)max_g);
     size_t chunks = op == OP_ED ? kEdTabChunks : kSwTabChunks;
     if (ensure_scratch(d, chunks * (size_t)max_g * kBlock)) return 1;
     switch (op) {
         case OP_K1:
-            ecrecover_kernel<CurveK1><<<grid, kBlock, 0, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, n, (Q4*)d_out,
-                                                              d_status, d.scratch, d.k1g);
+            ecrecover_kernel<CurveK1><<<grid, tpb, 0, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, n, (Q4*)d_out,
+                                                            d_status, d.scratch, d.k1g);
             break;
         case OP_R1:
-            ecrecover_kernel<CurveR1><<<grid, kBlock, 0, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, n, (Q4*)d_out,
-                                                              d_status, d.scratch, d.r1g);
+            ecrecover_kernel<CurveR1><<<grid, tpb, 0, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, n, (Q4*)d_out,
+                                                            d_status, d.scratch, d.r1g);
             break;
         case OP_ED:
-            ed25519_verify_kernel<<<grid, kBlock, 0, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, (const Q4*)d_pks, n,
-                                                           d_out, d.scratch, d.edb);
+            ed25519_verify_kernel<<<grid, tpb, 0, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, (const Q4*)d_pks, n,
+                                                         d_out, d.scratch, d.edb);
             break;
     }
     CK(cudaGetLastError());
@@ -200,33 +213,68 @@ int launch_op(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_msgs, co
     return 0;
 }
 
-// one shard on one device: H2D -> kernel -> D2H on the device's stream, timed with events
+// One shard on one device.  The shard is cut into up to kMaxChunks pieces that flow through a three-stage pipeline
+// (H2D on s_in, kernel on stream, D2H on s_out, chained with events), so that with pinned host buffers only the first
+// piece's upload and the last piece's download are exposed.  Kernels run back to back on ONE stream: they share the
+// per-thread scratch tables.
+constexpr int kMaxChunks = 8;
+constexpr size_t kMinWaves = 3;  // >= 3 passes (~7 ms of kernel) per piece
+
 int run_shard(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n, uint8_t* out,
               uint8_t* status) {
     CK(cudaSetDevice(d.id));
     const size_t in_bytes = n * (op == OP_ED ? 128 : 96);
-    const size_t out_main = op == OP_ED ? n : n * 64;
+    const size_t out_stride = op == OP_ED ? 1 : 64;
     const size_t out_bytes = op == OP_ED ? n : n * 65;
     if (ensure_buf(&d.d_in, &d.in_cap, in_bytes + 64)) return 1;
     if (ensure_buf(&d.d_out, &d.out_cap, out_bytes + 64)) return 1;
     uint8_t* d_sigs = d.d_in;
     uint8_t* d_msgs = d.d_in + n * 64;
     uint8_t* d_pks = d.d_in + n * 96;
-    CK(cudaEventRecord(d.ev[0], d.stream));
-    CK(cudaMemcpyAsync(d_sigs, sigs, n * 64, cudaMemcpyHostToDevice, d.stream));
-    CK(cudaMemcpyAsync(d_msgs, msgs, n * 32, cudaMemcpyHostToDevice, d.stream));
-    if (op == OP_ED) CK(cudaMemcpyAsync(d_pks, pks, n * 32, cudaMemcpyHostToDevice, d.stream));
-    CK(cudaEventRecord(d.ev[1], d.stream));
     uint8_t* d_status = op == OP_ED ? nullptr : d.d_out + n * 64;
-    if (launch_op(d, op, d_sigs, d_msgs, d_pks, n, d.d_out, d_status, d.stream)) return 1;
+    int max_chunks = kMaxChunks;
+    if (const char* e = getenv("SIGOPS_MAX_CHUNKS")) max_chunks = std::max(1, std::min(kMaxChunks, atoi(e)));
+    // pieces are whole multiples of one wave (SMs x 512 threads, one signature per thread per pass) so that only the
+    // last piece ends on a partial wave; at least kMinWaves waves per piece
+    const size_t wave = (size_t)d.sms * kBlock;
+    const size_t n_waves = (n + wave - 1) / wave;
+    int chunks = (int)std::min<size_t>((size_t)max_chunks, std::max<size_t>(1, n_waves / kMinWaves));
+    size_t bounds[kMaxChunks + 1];
+    for (int c = 0; c <= chunks; c++) bounds[c] = std::min(n, (n_waves * (size_t)c / chunks) * wave);
+    bounds[chunks] = n;
+    CK(cudaEventRecord(d.ev[0], d.s_in));
+    for (int c = 0; c < chunks; c++) {
+        const size_t lo = bounds[c], hi = bounds[c + 1], m = hi - lo;
+        CK(cudaMemcpyAsync(d_sigs + lo * 64, sigs + lo * 64, m * 64, cudaMemcpyHostToDevice, d.s_in));
+        CK(cudaMemcpyAsync(d_msgs + lo * 32, msgs + lo * 32, m * 32, cudaMemcpyHostToDevice, d.s_in));
+        if (op == OP_ED) CK(cudaMemcpyAsync(d_pks + lo * 32, pks + lo * 32, m * 32, cudaMemcpyHostToDevice, d.s_in));
+        CK(cudaEventRecord(d.ev_in[c], d.s_in));
+        CK(cudaStreamWaitEvent(d.stream, d.ev_in[c], 0));
+        if (c == 0) CK(cudaEventRecord(d.ev[1], d.stream));
+        if (launch_op(d, op, d_sigs + lo * 64, d_msgs + lo * 32, d_pks + lo * 32, m, d.d_out + lo * out_stride,
+                      d_status ? d_status + lo : nullptr, d.stream))
+            return 1;
+        CK(cudaEventRecord(d.ev_k[c], d.stream));
+    }
     CK(cudaEventRecord(d.ev[2], d.stream));
-    CK(cudaMemcpyAsync(out, d.d_out, out_main, cudaMemcpyDeviceToHost, d.stream));
-    if (op != OP_ED && status) CK(cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, d.stream));
-    CK(cudaEventRecord(d.ev[3], d.stream));
+    // downloads are enqueued after every upload and kernel: a download into pageable memory blocks the calling thread
+    // until its kernel has finished, which would otherwise stall the staging of the next piece's upload
+    for (int c = 0; c < chunks; c++) {
+        const size_t lo = bounds[c], hi = bounds[c + 1], m = hi - lo;
+        CK(cudaStreamWaitEvent(d.s_out, d.ev_k[c], 0));
+        CK(cudaMemcpyAsync(out + lo * out_stride, d.d_out + lo * out_stride, m * out_stride, cudaMemcpyDeviceToHost, d.s_out));
+        if (op != OP_ED && status) CK(cudaMemcpyAsync(status + lo, d_status + lo, m, cudaMemcpyDeviceToHost, d.s_out));
+    }
+    CK(cudaEventRecord(d.ev[3], d.s_out));
+    CK(cudaStreamSynchronize(d.s_out));
     CK(cudaStreamSynchronize(d.stream));
-    CK(cudaEventElapsedTime(&d.ms_h2d, d.ev[0], d.ev[1]));
+    CK(cudaStreamSynchronize(d.s_in));
+    // h2d: first upload until the first kernel may start; kernel: first kernel start to last kernel end (uploads and
+    // downloads of the other pieces overlap it); d2h: what remains after the last kernel
+    CK(cudaEventElapsedTime(&d.ms_h2d, d.ev[0], d.ev_in[0]));
     CK(cudaEventElapsedTime(&d.ms_kernel, d.ev[1], d.ev[2]));
     CK(cudaEventElapsedTime(&d.ms_d2h, d.ev[2], d.ev[3]));
+    if (d.ms_d2h < 0) d.ms_d2h = 0;
     return 0;
 }
 
@@ -359,7 +407,13 @@ int sigops_shutdown(void) {
         if (d.edb) cudaFree((void*)d.edb);
         for (auto& e : d.ev)
             if (e) cudaEventDestroy(e);
+        for (auto& e : d.ev_in)
+            if (e) cudaEventDestroy(e);
+        for (auto& e : d.ev_k)
+            if (e) cudaEventDestroy(e);
         if (d.stream) cudaStreamDestroy(d.stream);
+        if (d.s_in) cudaStreamDestroy(d.s_in);
+        if (d.s_out) cudaStreamDestroy(d.s_out);
     }
     g_dev.clear();
     g_inited = false;
