@@ -1,0 +1,18 @@
+//! Raw bindings of include/sigops.h (the C ABI of libsigops).  One `extern "C"` item per declaration of the header.
+use std::os::raw::{c_char, c_int, c_void};
+
+extern "C" {
+    pub fn sigops_init(device_ids: *const c_int, n_devices: c_int) -> c_int;
+    pub fn sigops_shutdown() -> c_int;
+    pub fn sigops_num_devices() -> c_int;
+    pub fn sigops_last_error() -> *const c_char;
+    pub fn sigops_secp256k1_ecrecover(sigs: *const u8, msgs: *const u8, n: usize, out_pubkeys: *mut u8, out_status: *mut u8) -> c_int;
+    pub fn sigops_secp256r1_ecrecover(sigs: *const u8, msgs: *const u8, n: usize, out_pubkeys: *mut u8, out_status: *mut u8) -> c_int;
+    pub fn sigops_ed25519_ecverify(sigs: *const u8, msgs: *const u8, pks: *const u8, n: usize, out_valid: *mut u8) -> c_int;
+    pub fn sigops_precompute_bases(curve: c_int, log_limb_size: u32, out: *mut u32, inout_len: *mut usize) -> c_int;
+    pub fn sigops_plan_shards(n: usize, n_devices: c_int, bounds: *mut usize, n_used: *mut c_int) -> c_int;
+    pub fn sigops_last_timing(h2d_ms: *mut f64, kernel_ms: *mut f64, d2h_ms: *mut f64) -> c_int;
+    pub fn sigops_kernel_launches() -> u64;
+    pub fn sigops_host_alloc(bytes: usize) -> *mut c_void;
+    pub fn sigops_host_free(p: *mut c_void);
+}
