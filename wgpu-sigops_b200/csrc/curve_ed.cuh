@@ -321,7 +321,7 @@ SG_HD bool ed_sqrt_ratio_i(Fe& r, const Fe& u, const Fe& v) {
 template <bool kSync>
 SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, const TabRef& tab, const u32* btab) {
     typedef Sc<ModEdL> S;
-#if defined(SG_HOT_INLINE)
+#if !defined(SG_NO_HOT_INLINE)
     typedef Inl<Fp25519> FH;  // products inlined: one doubling, one cached-addition and one Niels-addition site
 #else
     typedef Fp25519 FH;

@@ -61,10 +61,10 @@ struct CurveK1T {
     typedef FF F;
     typedef Sc<ModK1N> S;
     typedef CurveK1T<FpK1> Cold;
-#if defined(SG_HOT_INLINE)
+#if !defined(SG_NO_HOT_INLINE)
     typedef CurveK1T<Inl<FpK1> > Hot;
 #else
-    typedef CurveK1T<FpK1> Hot;  // measured on B200: inlining the products in the loop (86 KB body) thrashes the 32 KB L1.5 I-cache
+    typedef CurveK1T<FpK1> Hot;  // out-of-line products everywhere
 #endif
     static constexpr bool kGlv = true;
     static constexpr bool kAIsZero = true;
@@ -88,7 +88,7 @@ struct CurveR1T {
     typedef FF F;
     typedef Sc<ModR1N> S;
     typedef CurveR1T<FpR1> Cold;
-#if defined(SG_HOT_INLINE)
+#if !defined(SG_NO_HOT_INLINE)
     typedef CurveR1T<Inl<FpR1> > Hot;
 #else
     typedef CurveR1T<FpR1> Hot;

@@ -27,12 +27,14 @@ static constexpr int kBlock = SG_BLOCK;
 #define SG_MINB_ED 1
 #endif
 
-// Barriers inside the per-signature program (between its phases and per window of the main loop) on top of the one per
-// signature: measured 2-4% slower than the per-signature barrier alone, so off by default.
-#if defined(SG_INNER_SYNC)
-static constexpr bool kInnerSync = true;
-#else
+// Barriers inside the per-signature program (between its phases and once per window of the main loop) on top of the
+// one per signature.  Measured on B200 (profiles/r01_variants.md): with out-of-line products they cost 2-4%; together
+// with the loop's products inlined (SG_HOT_INLINE, a 70-86 KB loop body that all 16 warps then stream in lockstep) they
+// win 3-5%.  Both are on by default; -DSG_NO_HOT_INLINE / -DSG_NO_INNER_SYNC switch them off.
+#if defined(SG_NO_INNER_SYNC)
 static constexpr bool kInnerSync = false;
+#else
+static constexpr bool kInnerSync = true;
 #endif
 
 #if defined(__CUDACC__)
