@@ -16,7 +16,7 @@ def test_field_ed25519(sim_units):
 
 
 def test_field_r1(sim_units):
-    uc.check_field(sim_units, "R1", o.R1.p, False)
+    uc.check_field(sim_units, "R1", o.R1.p, True)
 
 
 def test_wide_products(sim_units):

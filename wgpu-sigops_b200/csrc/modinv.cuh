@@ -224,7 +224,9 @@ SG_HD void fe_inv(Fp25519*, Fe& r, const Fe& a) {
 // Montgomery domain: a = x R  ->  (x R)^-1 = x^-1 R^-1;  times R^3 (one Montgomery product) = x^-1 R
 SG_HD void fe_inv(FpR1*, Fe& r, const Fe& a) {
     const Fe R3 = {SG_R1_P_R3};
-    Fe t = ModInv<ModInvR1P>::inv_(a);
+    Fe n;
+    FpR1::normalize(n, a);
+    Fe t = ModInv<ModInvR1P>::inv_(n);
     FpR1::mul(r, t, R3);
 }
 
