@@ -412,7 +412,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="sigops", choices=["sigops", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--pool", type=int, default=262144, help="unique signatures generated per curve, tiled to --batch")
+    ap.add_argument("--pool", type=int, default=BATCH, help="unique signatures generated per curve (tiled to --batch if smaller)")
     ap.add_argument("--curves", default="all")
     ap.add_argument("--cpu-sample", type=int, default=131072)
     ap.add_argument("--ref-sample", type=int, default=65536)

@@ -834,88 +834,166 @@ static void prng_scalar(const mctx* fn, fe* k, u64 seed, u64 curve, u64 index, u
 
 #define KEY_POOL 4096
 
-/* signature i: key = pool[i % KEY_POOL], message = PRNG, nonce = PRNG; low-s normalised when low_s (as
- * `Signature::sign` does); the y parity of R goes to bit 7 of byte 32.  pks receives the signer's key X||Y. */
+/* Montgomery's trick: out[i] = v[i]^-1 for nonzero Montgomery-domain values (one m_inv per call) */
+static void batch_inv(const mctx* c, fe* out, const fe* v, size_t n) {
+    if (!n) return;
+    out[0] = v[0];
+    for (size_t i = 1; i < n; i++) m_mul(c, &out[i], &out[i - 1], &v[i]);
+    fe inv;
+    m_inv(c, &inv, &out[n - 1]);
+    for (size_t i = n - 1; i > 0; i--) {
+        fe t;
+        m_mul(c, &t, &inv, &out[i - 1]);
+        m_mul(c, &inv, &inv, &v[i]);
+        out[i] = t;
+    }
+    out[0] = inv;
+}
+
+#define GEN_BLOCK 256
+
+/* Signature i: key = pool[i % KEY_POOL], message = PRNG(i), nonce k_i = k_b + (i - b) where b is the first index of i's
+ * block of GEN_BLOCK signatures and k_b = PRNG(b): R_i = R_(i-1) + G costs one point addition, and the affine
+ * conversions and the k^-1 share one inversion per block (the scheme SURVEY.md 8d proposes for the 1M-row batches).
+ * How a nonce was chosen is invisible to a verifier: these are ordinary valid signatures of random keys and messages.
+ * s is low-s normalised when low_s (as `Signature::sign` does); the y parity of R goes to bit 7 of byte 32; pks
+ * receives the signer's key X||Y. */
 static void sw_gen_range(const swcurve* c, int curve_id, u64 seed, size_t lo, size_t hi, int low_s, uint8_t* sigs,
                          uint8_t* msgs, uint8_t* pks, const fe* pool_d, const uint8_t* pool_pk) {
     const mctx *fp = &c->fp, *fn = &c->fn;
-    for (size_t i = lo; i < hi; i++) {
-        size_t kidx = i % KEY_POOL;
-        uint8_t* sig = sigs + 64 * i;
-        uint8_t* msg = msgs + 32 * i;
-        prng32(msg, seed, (u64)curve_id, i, 1);
+    jac G;
+    jac_from_aff(c, &G, &c->g, 0);
+    fe one_n = {{1, 0, 0, 0}};
+    for (size_t base = lo - lo % GEN_BLOCK; base < hi; base += GEN_BLOCK) {
         for (u64 attempt = 0;; attempt++) {
-            fe k, z, r, s, t;
-            prng_scalar(fn, &k, seed, (u64)curve_id, i, 2 + attempt);
-            jac Rj;
-            sw_double_mul(c, &Rj, &k, NULL, NULL);
-            aff Ra;
-            jac_to_aff(c, &Ra, &Rj);
-            fe rx, ry;
-            m_from(fp, &rx, &Ra.x);
-            m_from(fp, &ry, &Ra.y);
-            if (fe_gte(&rx, &fn->m) || fe_is_zero(&rx)) continue; /* x >= n is not encodable in the Fuel format */
-            r = rx;
-            fe_from_be(&z, msg);
-            if (fe_gte(&z, &fn->m)) fe_sub_raw(&z, &z, &fn->m);
-            /* s = k^-1 (z + r d) mod n */
-            fe km, kinv, rm, dm, zm;
-            m_to(fn, &km, &k);
-            m_inv(fn, &kinv, &km);
-            m_to(fn, &rm, &r);
-            m_to(fn, &dm, &pool_d[kidx]);
-            m_to(fn, &zm, &z);
-            m_mul(fn, &t, &rm, &dm);
-            m_add(fn, &t, &t, &zm);
-            m_mul(fn, &s, &t, &kinv);
-            m_from(fn, &s, &s);
-            if (fe_is_zero(&s)) continue;
-            int parity = (int)(ry.v[0] & 1);
-            fe ns;
-            fe_sub_raw(&ns, &fn->m, &s);
-            int high = fe_gte(&s, &ns); /* s > n/2 (n odd so s != n - s) */
-            if (low_s && high) {
-                s = ns;
-                parity ^= 1;
+            fe k0;
+            prng_scalar(fn, &k0, seed, (u64)curve_id, base, 2 + attempt);
+            jac P;
+            sw_double_mul(c, &P, &k0, NULL, NULL);
+            fe zs[GEN_BLOCK], zinv[GEN_BLOCK], km[GEN_BLOCK], kinv[GEN_BLOCK];
+            jac pts[GEN_BLOCK];
+            int ok = 1;
+            fe k = k0;
+            for (int j = 0; j < GEN_BLOCK; j++) {
+                if (P.inf || fe_is_zero(&k)) ok = 0;
+                pts[j] = P;
+                zs[j] = P.Z;
+                m_to(fn, &km[j], &k);
+                jac_add(c, &P, &G);
+                m_add(fn, &k, &k, &one_n);
             }
-            if (s.v[3] >> 63) { /* only s < 2^255 is encodable: flip to the other representative */
-                fe_sub_raw(&s, &fn->m, &s);
-                parity ^= 1;
+            if (!ok) continue; /* the block would cross k = 0 mod n: probability ~2^-248 */
+            batch_inv(fp, zinv, zs, GEN_BLOCK);
+            batch_inv(fn, kinv, km, GEN_BLOCK);
+            fe rxs[GEN_BLOCK];
+            int par[GEN_BLOCK];
+            for (int j = 0; j < GEN_BLOCK; j++) {
+                fe zi2, ax, ay, ry;
+                m_sqr(fp, &zi2, &zinv[j]);
+                m_mul(fp, &ax, &pts[j].X, &zi2);
+                m_mul(fp, &zi2, &zi2, &zinv[j]);
+                m_mul(fp, &ay, &pts[j].Y, &zi2);
+                m_from(fp, &rxs[j], &ax);
+                m_from(fp, &ry, &ay);
+                par[j] = (int)(ry.v[0] & 1);
+                /* x >= n (probability 2^-128) is not encodable in the Fuel format (no "x reduced" recovery id) */
+                if (fe_gte(&rxs[j], &fn->m) || fe_is_zero(&rxs[j])) ok = 0;
             }
-            fe_to_be(sig, &r);
-            fe_to_be(sig + 32, &s);
-            sig[32] |= (uint8_t)(parity << 7);
+            if (!ok) continue;
+            for (int j = 0; j < GEN_BLOCK; j++) {
+                size_t i = base + (size_t)j;
+                if (i < lo || i >= hi) continue;
+                size_t kidx = i % KEY_POOL;
+                uint8_t* sig = sigs + 64 * i;
+                uint8_t* msg = msgs + 32 * i;
+                fe z, r = rxs[j], s, t, rm, dm, zm;
+                for (u64 retry = 0;; retry++) {
+                    prng32(msg, seed, (u64)curve_id, i, 1 + 64 * retry);
+                    fe_from_be(&z, msg);
+                    if (fe_gte(&z, &fn->m)) fe_sub_raw(&z, &z, &fn->m);
+                    /* s = k^-1 (z + r d) mod n */
+                    m_to(fn, &rm, &r);
+                    m_to(fn, &dm, &pool_d[kidx]);
+                    m_to(fn, &zm, &z);
+                    m_mul(fn, &t, &rm, &dm);
+                    m_add(fn, &t, &t, &zm);
+                    m_mul(fn, &s, &t, &kinv[j]);
+                    m_from(fn, &s, &s);
+                    if (!fe_is_zero(&s)) break; /* s == 0 (probability 2^-256): another message */
+                }
+                int parity = par[j];
+                fe ns;
+                fe_sub_raw(&ns, &fn->m, &s);
+                int high = fe_gte(&s, &ns); /* s > n/2 (n odd so s != n - s) */
+                if (low_s && high) {
+                    s = ns;
+                    parity ^= 1;
+                }
+                if (s.v[3] >> 63) { /* only s < 2^255 is encodable: flip to the other representative */
+                    fe_sub_raw(&s, &fn->m, &s);
+                    parity ^= 1;
+                }
+                fe_to_be(sig, &r);
+                fe_to_be(sig + 32, &s);
+                sig[32] |= (uint8_t)(parity << 7);
+                if (pks) memcpy(pks + 64 * i, pool_pk + 64 * kidx, 64);
+            }
             break;
         }
-        if (pks) memcpy(pks + 64 * i, pool_pk + 64 * kidx, 64);
     }
 }
 
+/* ed25519: same block scheme with r_i = r_b + (i - b) (any r yields a valid signature R = [r]B, s = r + k a). */
 static void ed_gen_range(u64 seed, size_t lo, size_t hi, uint8_t* sigs, uint8_t* msgs, uint8_t* pks, const fe* pool_a,
                          const uint8_t* pool_prefix, const uint8_t* pool_pk) {
-    const mctx* fl = &ED.fl;
-    for (size_t i = lo; i < hi; i++) {
-        size_t kidx = i % KEY_POOL;
-        uint8_t* sig = sigs + 64 * i;
-        uint8_t* msg = msgs + 32 * i;
-        prng32(msg, seed, 2, i, 1);
-        uint8_t h[64];
-        fe r, k, s, am, km;
-        sha512_3(h, pool_prefix + 32 * kidx, 32, msg, 32, NULL, 0);
-        ed_reduce512(&r, h);
-        edp Rp;
-        ed_double_mul(&Rp, &r, NULL, NULL, 0);
-        ed_compress(sig, &Rp);
-        sha512_3(h, sig, 32, pool_pk + 32 * kidx, 32, msg, 32);
-        ed_reduce512(&k, h);
-        /* s = r + k*a mod L  (a reduced mod L first) */
-        m_to(fl, &am, &pool_a[kidx]);
-        m_to(fl, &km, &k);
-        m_mul(fl, &s, &km, &am);
-        m_from(fl, &s, &s);
-        m_add(fl, &s, &s, &r);
-        fe_to_le(sig + 32, &s);
-        memcpy(pks + 32 * i, pool_pk + 32 * kidx, 32);
+    const mctx *fl = &ED.fl, *fp = &ED.fp;
+    (void)pool_prefix;
+    fe one_l = {{1, 0, 0, 0}};
+    for (size_t base = lo - lo % GEN_BLOCK; base < hi; base += GEN_BLOCK) {
+        uint8_t rb[64];
+        memset(rb, 0, sizeof rb);
+        prng32(rb, seed, 2, base, 2);
+        prng32(rb + 32, seed, 2, base, 3);
+        fe r;
+        ed_reduce512(&r, rb);
+        edp P;
+        ed_double_mul(&P, &r, NULL, NULL, 0);
+        fe rs[GEN_BLOCK], zs[GEN_BLOCK], zinv[GEN_BLOCK];
+        edp pts[GEN_BLOCK];
+        for (int j = 0; j < GEN_BLOCK; j++) {
+            pts[j] = P;
+            rs[j] = r;
+            zs[j] = P.Z; /* never zero: the formulas are complete */
+            ed_add(&P, &ED.B, 0);
+            m_add(fl, &r, &r, &one_l);
+        }
+        batch_inv(fp, zinv, zs, GEN_BLOCK);
+        for (int j = 0; j < GEN_BLOCK; j++) {
+            size_t i = base + (size_t)j;
+            if (i < lo || i >= hi) continue;
+            size_t kidx = i % KEY_POOL;
+            uint8_t* sig = sigs + 64 * i;
+            uint8_t* msg = msgs + 32 * i;
+            prng32(msg, seed, 2, i, 1);
+            fe x, y, k, s, am, km;
+            m_mul(fp, &x, &pts[j].X, &zinv[j]);
+            m_mul(fp, &y, &pts[j].Y, &zinv[j]);
+            m_from(fp, &x, &x);
+            m_from(fp, &y, &y);
+            fe_to_le(sig, &y);
+            sig[31] |= (uint8_t)((x.v[0] & 1) << 7);
+            uint8_t h[64];
+            sha512_3(h, sig, 32, pool_pk + 32 * kidx, 32, msg, 32);
+            ed_reduce512(&k, h);
+            /* s = r + k*a mod L */
+            m_to(fl, &am, &pool_a[kidx]);
+            m_to(fl, &km, &k);
+            m_mul(fl, &s, &km, &am);
+            m_from(fl, &s, &s);
+            m_add(fl, &s, &s, &rs[j]);
+            fe_to_le(sig + 32, &s);
+            memcpy(pks + 32 * i, pool_pk + 32 * kidx, 32);
+        }
     }
 }
 
