@@ -114,7 +114,8 @@ int sigops_test_unit_shape(int op, int* in_words, int* out_words);
 
 /* Integer-pipe micro-benchmark: independent multiply-add chains at full occupancy on every SM of the current
  * device.  kind 0 = IMAD (32-bit mad.lo), 1 = IMAD.WIDE.U32 (mad.wide), 2 = IMAD.WIDE.U32.X carry chains
- * (mad.lo.cc/madc.hi.cc), 3 = IADD3 (add), 4 = mixed 1:1 IMAD.WIDE + IADD3.  Returns the measured rate in
+ * (mad.lo.cc/madc.hi.cc), 3 = IADD3 (add), 4 = mixed 1:1 IMAD.WIDE + IADD3, 5 = DFMA (fma.rn.f64), 6 = IMAD.HI
+ * (mad.hi.u32).  Returns the measured rate in
  * instructions (thread-level operations) per second in *ops_per_sec, elapsed GPU time in *ms. */
 int sigops_imad_peak(int kind, int iters, double* ops_per_sec, double* ms);
 

@@ -21,7 +21,7 @@ def main():
     lib = w.load()
     res = {"n": n}
     ops, ms = ctypes.c_double(), ctypes.c_double()
-    names = {0: "imad", 1: "imad_wide", 2: "imad_wide_x_chain", 3: "iadd", 4: "imad_wide_plus_iadd"}
+    names = {0: "imad", 1: "imad_wide", 2: "imad_wide_x_chain", 3: "iadd", 4: "imad_wide_plus_iadd", 5: "dfma", 6: "imad_hi"}
     for kind, name in names.items():
         rc = lib.sigops_imad_peak(kind, 4096, ctypes.byref(ops), ctypes.byref(ms))
         assert rc == 0, lib.sigops_last_error()

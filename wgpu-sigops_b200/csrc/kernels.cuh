@@ -461,6 +461,27 @@ __global__ void __launch_bounds__(256) imad_peak_kernel(u32* sink, int iters, u3
                     : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7), "+r"(b0),
                       "+r"(b1), "+r"(b2), "+r"(b3), "+r"(b4), "+r"(b5), "+r"(b6), "+r"(b7)
                     : "r"(x), "r"(y));
+            } else if (KIND == 5) {
+                // FP64 pipe: 8 independent DFMA chains (the a/b registers are reinterpreted pairwise as doubles)
+                asm volatile(
+                    "{.reg .f64 d0,d1,d2,d3,d4,d5,d6,d7,m;\n\t"
+                    "mov.b64 d0,{%0,%8}; mov.b64 d1,{%1,%9}; mov.b64 d2,{%2,%10}; mov.b64 d3,{%3,%11};\n\t"
+                    "mov.b64 d4,{%4,%12}; mov.b64 d5,{%5,%13}; mov.b64 d6,{%6,%14}; mov.b64 d7,{%7,%15};\n\t"
+                    "mov.b64 m,{%16,%17};\n\t"
+                    "fma.rn.f64 d0,d0,m,m; fma.rn.f64 d1,d1,m,m; fma.rn.f64 d2,d2,m,m; fma.rn.f64 d3,d3,m,m;\n\t"
+                    "fma.rn.f64 d4,d4,m,m; fma.rn.f64 d5,d5,m,m; fma.rn.f64 d6,d6,m,m; fma.rn.f64 d7,d7,m,m;\n\t"
+                    "mov.b64 {%0,%8},d0; mov.b64 {%1,%9},d1; mov.b64 {%2,%10},d2; mov.b64 {%3,%11},d3;\n\t"
+                    "mov.b64 {%4,%12},d4; mov.b64 {%5,%13},d5; mov.b64 {%6,%14},d6; mov.b64 {%7,%15},d7;}"
+                    : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7), "+r"(b0),
+                      "+r"(b1), "+r"(b2), "+r"(b3), "+r"(b4), "+r"(b5), "+r"(b6), "+r"(b7)
+                    : "r"(x), "r"(y));
+            } else if (KIND == 6) {
+                asm volatile(
+                    "mad.hi.u32 %0, %0, %8, %9;\n\tmad.hi.u32 %1, %1, %8, %9;\n\tmad.hi.u32 %2, %2, %8, %9;\n\t"
+                    "mad.hi.u32 %3, %3, %8, %9;\n\tmad.hi.u32 %4, %4, %8, %9;\n\tmad.hi.u32 %5, %5, %8, %9;\n\t"
+                    "mad.hi.u32 %6, %6, %8, %9;\n\tmad.hi.u32 %7, %7, %8, %9;"
+                    : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7)
+                    : "r"(x), "r"(y));
             } else if (KIND == 3) {
                 asm volatile(
                     "add.u32 %0, %0, %8;\n\tadd.u32 %1, %1, %9;\n\tadd.u32 %2, %2, %8;\n\tadd.u32 %3, %3, %9;\n\t"

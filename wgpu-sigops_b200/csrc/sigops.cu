@@ -25,11 +25,15 @@ using namespace sigops;
 
 namespace {
 
-std::mutex g_mu;
+std::mutex g_mu;      // serialises the entry points
+std::mutex g_err_mu;  // shard threads may report errors concurrently
 std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 
-void set_err(const std::string& s) { g_err = s; }
+void set_err(const std::string& s) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    g_err = s;
+}
 
 #define CK(call)                                                                                       \
     do {                                                                                               \
@@ -278,6 +282,30 @@ int run_shard(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs, const 
     return 0;
 }
 
+// A device's shard is processed in sub-shards of at most kMaxSubShard signatures so that the device buffers stay
+// bounded (2 GiB in, 1 GiB out) however large the batch (the reference allows up to 2^30 signatures per call,
+// src/secp256k1_ecdsa.rs:22).  Timings accumulate over the sub-shards.
+constexpr size_t kMaxSubShard = (size_t)1 << 24;
+
+int run_shard_bounded(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n,
+                      uint8_t* out, uint8_t* status) {
+    const size_t out_stride = op == OP_ED ? 1 : 64;
+    float h2d = 0, ker = 0, d2h = 0;
+    for (size_t lo = 0; lo < n; lo += kMaxSubShard) {
+        const size_t m = std::min(kMaxSubShard, n - lo);
+        if (int rc = run_shard(d, op, sigs + lo * 64, msgs + lo * 32, pks ? pks + lo * 32 : nullptr, m,
+                               out + lo * out_stride, status ? status + lo : nullptr))
+            return rc;
+        h2d += d.ms_h2d;
+        ker += d.ms_kernel;
+        d2h += d.ms_d2h;
+    }
+    d.ms_h2d = h2d;
+    d.ms_kernel = ker;
+    d.ms_d2h = d2h;
+    return 0;
+}
+
 // below this many signatures per device a shard is not worth a GPU of its own (launch + sync latency dominates)
 constexpr size_t kMinShard = 4096;
 
@@ -303,13 +331,13 @@ int run_batch(Op op, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pk
     std::vector<size_t> bounds(g_dev.size() + 1);
     const size_t G = (size_t)plan_shards(n, (int)g_dev.size(), bounds.data());
     const size_t out_stride = op == OP_ED ? 1 : 64;
-    if (G == 1) return run_shard(g_dev[0], op, sigs, msgs, pks, n, out, status);
+    if (G == 1) return run_shard_bounded(g_dev[0], op, sigs, msgs, pks, n, out, status);
     std::vector<int> rcs(G, 0);
     std::vector<std::thread> th;
     for (size_t g = 0; g < G; g++) {
         const size_t lo = bounds[g], hi = bounds[g + 1];  // contiguous shard [lo, hi)
         th.emplace_back([&, g, lo, hi]() {
-            rcs[g] = run_shard(g_dev[g], op, sigs + lo * 64, msgs + lo * 32, pks ? pks + lo * 32 : nullptr, hi - lo,
+            rcs[g] = run_shard_bounded(g_dev[g], op, sigs + lo * 64, msgs + lo * 32, pks ? pks + lo * 32 : nullptr, hi - lo,
                                out + lo * out_stride, status ? status + lo : nullptr);
         });
     }
@@ -426,7 +454,13 @@ int sigops_num_devices(void) {
     return (int)g_dev.size();
 }
 
-const char* sigops_last_error(void) { return g_err.c_str(); }
+const char* sigops_last_error(void) {
+    // a stable copy: the shared string may be rewritten by a concurrent failing call
+    static thread_local std::string copy;
+    std::lock_guard<std::mutex> lk(g_err_mu);
+    copy = g_err;
+    return copy.c_str();
+}
 
 int sigops_secp256k1_ecrecover(const uint8_t* sigs, const uint8_t* msgs, size_t n, uint8_t* out_pubkeys,
                                uint8_t* out_status) {
@@ -598,6 +632,8 @@ int sigops_imad_peak(int kind, int iters, double* ops_per_sec, double* ms_out) {
             case 2: imad_peak_kernel<2><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
             case 3: imad_peak_kernel<3><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
             case 4: imad_peak_kernel<4><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
+            case 5: imad_peak_kernel<5><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
+            case 6: imad_peak_kernel<6><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
             default: set_err("bad kind"); return 1;
         }
         CK(cudaGetLastError());
@@ -607,7 +643,8 @@ int sigops_imad_peak(int kind, int iters, double* ops_per_sec, double* ms_out) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
     // counted operations per thread per outer iteration (16 unrolled blocks):
-    //  kind 0: 8 IMAD; 1: 8 IMAD.WIDE; 2: 8 IMAD.WIDE(.X); 3: 8 IADD; 4: 8 IMAD.WIDE + 8 IADD (counted: the 8 wide)
+    //  kind 0: 8 IMAD; 1: 8 IMAD.WIDE; 2: 8 IMAD.WIDE(.X); 3: 8 IADD; 4: 8 IMAD.WIDE + 8 IADD (counted: the 8 wide);
+    //  5: 8 DFMA; 6: 8 IMAD.HI
     per_thread_iter = 16.0 * 8.0;
     double ops = per_thread_iter * (double)iters * (double)grid * block;
     if (ops_per_sec) *ops_per_sec = ops / (ms * 1e-3);
