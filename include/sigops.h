@@ -69,6 +69,16 @@ int sigops_secp256r1_ecrecover(const uint8_t* sigs, const uint8_t* msgs, size_t 
 int sigops_ed25519_ecverify(const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n,
                             uint8_t* out_valid);
 
+/* ed25519 with variable-length messages and optional strict semantics -- the form fuel_crypto::ed25519::verify needs
+ * (ed25519-dalek `verify_strict` over arbitrary-length messages); the reference hard-wires 32-byte messages and the
+ * 96-byte hash input (src/wgsl/sha512.wgsl:114-123, src/wgsl/main/ed25519_eddsa_main_0.wgsl:40-85) and tests the
+ * non-strict `verify` (src/tests/ed25519_eddsa.rs:26; strictness noted at src/curve_algos/ed25519_eddsa.rs:196-198).
+ * msg_bytes: the messages back to back; msg_offsets: n + 1 byte offsets, message i = [msg_offsets[i], msg_offsets[i+1]).
+ * flags: SIGOPS_ED25519_STRICT additionally requires that R decompresses and that neither A nor R has small order. */
+#define SIGOPS_ED25519_STRICT 1u
+int sigops_ed25519_ecverify_msgs(const uint8_t* sigs, const uint8_t* msg_bytes, const uint64_t* msg_offsets,
+                                 const uint8_t* pks, size_t n, uint32_t flags, uint8_t* out_valid);
+
 /* precompute::{secp256k1_bases, secp256r1_bases, ed25519_bases}  (src/precompute.rs:12,36-69).
  * CPU-only compatibility table: 16 multiples (i+1)*G, coordinates in Montgomery form with
  * R = 2^(num_limbs*log_limb_size), little-endian log_limb_size-bit limbs; x||y per entry for the secp curves

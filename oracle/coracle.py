@@ -52,6 +52,8 @@ def load() -> ctypes.CDLL:
         lib.oracle_gen_ecdsa.argtypes = [i32, u64, sz, i32, vp, vp, vp, i32]
         lib.oracle_gen_ed25519.argtypes = [u64, sz, vp, vp, vp, i32]
         lib.oracle_sha512.argtypes = [vp, sz, vp]
+        lib.oracle_ed25519_verify_msgs.argtypes = [vp, vp, vp, vp, sz, i32, vp]
+        lib.oracle_ed25519_sign.argtypes = [vp, vp, sz, vp, vp]
         _lib = lib
     return _lib
 
@@ -126,3 +128,34 @@ def sha512(msg: bytes) -> bytes:
     buf = np.frombuffer(msg, dtype=np.uint8) if msg else np.zeros(1, dtype=np.uint8)
     assert load().oracle_sha512(buf.ctypes.data, len(msg), out.ctypes.data) == 0
     return out.tobytes()
+
+
+def _blob(messages):
+    offs = np.zeros(len(messages) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(m) for m in messages], dtype=np.uint64)
+    blob = np.frombuffer(b"".join(bytes(m) for m in messages) or b"\0", dtype=np.uint8)
+    return blob, offs
+
+
+def ecverify_ed25519_msgs(sigs, messages, pks, strict: bool = False):
+    """dalek `verify` / `verify_strict` over messages of any length (list of bytes)."""
+    sigs, pks = _u8(sigs, 64), _u8(pks, 32)
+    n = sigs.shape[0]
+    assert n == pks.shape[0] == len(messages)
+    out = np.zeros(n, dtype=np.uint8)
+    if n:
+        blob, offs = _blob(messages)
+        rc = load().oracle_ed25519_verify_msgs(sigs.ctypes.data, blob.ctypes.data, offs.ctypes.data, pks.ctypes.data, n,
+                                               int(strict), out.ctypes.data)
+        assert rc == 0
+    return out
+
+
+def ed25519_sign(seed: bytes, msg: bytes):
+    """RFC 8032 signature of an arbitrary-length message: (sig 64 B, pk 32 B)."""
+    sig = np.zeros(64, dtype=np.uint8)
+    pk = np.zeros(32, dtype=np.uint8)
+    s = np.frombuffer(seed, dtype=np.uint8)
+    m = np.frombuffer(msg, dtype=np.uint8) if msg else np.zeros(1, dtype=np.uint8)
+    assert load().oracle_ed25519_sign(s.ctypes.data, m.ctypes.data, len(msg), sig.ctypes.data, pk.ctypes.data) == 0
+    return sig.tobytes(), pk.tobytes()

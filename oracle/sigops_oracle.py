@@ -325,6 +325,33 @@ def ecverify_ed25519(sig: bytes, msg: bytes, pk: bytes) -> bool:
     return ed_compress(Rp) == sig[:32]
 
 
+def ed_is_small_order(P: EdPoint) -> bool:
+    """curve25519-dalek `is_small_order`: [8]P is the identity."""
+    Q = ed_mul(8, P)
+    return Q[0] % ED_P == 0 and (Q[1] - Q[2]) % ED_P == 0
+
+
+def ecverify_ed25519_strict(sig: bytes, msg: bytes, pk: bytes) -> bool:
+    """ed25519-dalek 2.1.1 `VerifyingKey::verify_strict` (what fuel_crypto::ed25519::verify calls; noted in the reference
+    at src/curve_algos/ed25519_eddsa.rs:196-198): as `verify`, and in addition the signature's R must decompress and
+    neither A nor R may have small order.  Messages of any length."""
+    assert len(sig) == 64 and len(pk) == 32
+    A = ed_decompress(pk)
+    if A is None:
+        return False
+    s = int.from_bytes(sig[32:], "little")
+    if s >= ED_L:
+        return False
+    Rpt = ed_decompress(sig[:32])
+    if Rpt is None:
+        return False
+    if ed_is_small_order(Rpt) or ed_is_small_order(A):
+        return False
+    k = ed_challenge(sig[:32], pk, msg)
+    Rp = ed_add(ed_mul(s, ED_B), ed_mul(k, ed_neg(A)))
+    return ed_compress(Rp) == sig[:32]
+
+
 def ed25519_expand(seed: bytes) -> Tuple[int, bytes, bytes]:
     h = hashlib.sha512(seed).digest()
     a = int.from_bytes(h[:32], "little")

@@ -77,4 +77,19 @@ int hostsim_ed25519_verify(const uint8_t* sigs, const uint8_t* msgs, const uint8
     }
     return 0;
 }
+
+int hostsim_ed25519_verify_msgs(const uint8_t* sigs, const uint8_t* msg_bytes, const uint64_t* off, const uint8_t* pks, size_t n,
+                                int strict, uint8_t* valid) {
+    ensure_tables();
+    std::vector<Q4> scratch(kEdTabChunks);
+    TabRef tab{scratch.data(), 1};
+    for (size_t i = 0; i < n; i++) {
+        u32 sig_w[16], pk_w[8];
+        memcpy(sig_w, sigs + 64 * i, 64);
+        memcpy(pk_w, pks + 32 * i, 32);
+        valid[i] = (uint8_t)ed_verify_msg<false>(sig_w, msg_bytes + off[i], (size_t)(off[i + 1] - off[i]), pk_w, strict != 0, tab,
+                                                 ed_btab.data());
+    }
+    return 0;
+}
 }

@@ -1,0 +1,105 @@
+"""ed25519 with variable-length messages and ed25519-dalek `verify_strict` semantics (what
+fuel_crypto::ed25519::verify uses).  CPU part: the oracles against RFC 8032 / OpenSSL and each other, and the CUDA
+headers compiled for the host.  GPU part: `sigops_ed25519_ecverify_msgs` through the Python mirror."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import coracle
+import sigops_oracle as o
+import strict_cases
+from simlib import load_hostsim
+
+
+def _expected(cases, strict):
+    f = o.ecverify_ed25519_strict if strict else o.ecverify_ed25519
+    return [f(s, m, pk) for _, s, m, pk in cases]
+
+
+def test_oracles_agree_and_strict_differs():
+    cs = strict_cases.cases()
+    for strict in (False, True):
+        exp = _expected(cs, strict)
+        got = coracle.ecverify_ed25519_msgs([c[1] for c in cs], [c[2] for c in cs], [c[3] for c in cs], strict)
+        for c, e, g in zip(cs, exp, got):
+            assert bool(g) == e, (c[0], strict)
+    lax, strict = _expected(cs, False), _expected(cs, True)
+    assert all(a or not b for a, b in zip(lax, strict))  # strict accepts a subset
+    flipped = [c[0] for c, a, b in zip(cs, lax, strict) if a and not b]
+    assert any("small_order_A" in x for x in flipped) and any("A_ident" in x or "A_order2" in x for x in flipped)
+
+
+def test_rfc8032_and_openssl_variable_length():
+    from cryptography.hazmat.primitives import serialization
+    from cryptography.hazmat.primitives.asymmetric import ed25519
+
+    # RFC 8032 7.1 TEST 2 and TEST 3 (1- and 2-byte messages) under both semantics
+    for pk, msg, sig in (
+        ("3d4017c3e843895a92b70aa74d1b7ebc9c982ccf2ec4968cc0cd55f12af4660c", "72",
+         "92a009a9f0d4cab8720e820b5f642540a2b27b5416503f8fb3762223ebdb69da085ac1e43e15996e458f3613d0f11d8c387b2eaeb4302aeeb00d291612bb0c00"),
+        ("fc51cd8e6218a1a38da47ed00230f0580816ed13ba3303ac5deb911548908025", "af82",
+         "6291d657deec24024827e69c3abe01a30ce548a284743a445e3680d7db5ac3ac18ff9b538d16f290ae67f760984dc6594a7c15e9716ed28dc027beceea1ec40a"),
+    ):
+        pk, msg, sig = bytes.fromhex(pk), bytes.fromhex(msg), bytes.fromhex(sig)
+        assert o.ecverify_ed25519_strict(sig, msg, pk) and coracle.ecverify_ed25519_msgs([sig], [msg], [pk], True)[0]
+    for ln in (0, 5, 200, 3000):
+        key = ed25519.Ed25519PrivateKey.generate()
+        msg = hashlib.shake_128(b"m%d" % ln).digest(ln)
+        sig = key.sign(msg)
+        pk = key.public_key().public_bytes(serialization.Encoding.Raw, serialization.PublicFormat.Raw)
+        assert coracle.ecverify_ed25519_msgs([sig], [msg], [pk], True)[0] == 1
+        s2, pk2 = coracle.ed25519_sign(b"\x07" * 32, msg)
+        ed25519.Ed25519PublicKey.from_public_bytes(pk2).verify(s2, msg)
+
+
+def _blob(cs):
+    offs = np.zeros(len(cs) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(c[2]) for c in cs], dtype=np.uint64)
+    return b"".join(c[2] for c in cs) or b"\0", offs
+
+
+def test_hostsim_matches_oracle():
+    lib = load_hostsim()
+    cs = strict_cases.cases()
+    blob, offs = _blob(cs)
+    for strict in (0, 1):
+        out = np.zeros(len(cs), dtype=np.uint8)
+        lib.hostsim_ed25519_verify_msgs(b"".join(c[1] for c in cs), blob, offs.ctypes.data, b"".join(c[3] for c in cs), len(cs),
+                                        strict, out.ctypes.data)
+        for c, e, g in zip(cs, _expected(cs, bool(strict)), out):
+            assert bool(g) == e, (c[0], strict)
+
+
+@pytest.mark.gpu
+def test_gpu_strict_and_variable_length(sigops):
+    cs = strict_cases.cases()
+    for strict in (False, True):
+        got = sigops.ed25519_eddsa.ecverify_msgs([c[1] for c in cs], [c[2] for c in cs], [c[3] for c in cs], strict=strict)
+        for c, e, g in zip(cs, _expected(cs, strict), got):
+            assert bool(g) == e, (c[0], strict)
+    assert sigops.ed25519_eddsa.ecverify_strict([cs[0][1]], [cs[0][2]], [cs[0][3]]) == [True]
+    assert len(sigops.ed25519_eddsa.ecverify_msgs([], [], [])) == 0
+
+
+@pytest.mark.gpu
+def test_gpu_strict_batch_ragged_lengths(sigops):
+    """20,000 signatures over messages of 0..300 bytes, a third corrupted: every verdict equals the C oracle's."""
+    import random
+
+    rng = random.Random(5)
+    n = 20000
+    keys = [bytes(rng.getrandbits(8) for _ in range(32)) for _ in range(64)]
+    sigs, msgs, pks = [], [], []
+    for i in range(n):
+        msg = bytes(rng.getrandbits(8) for _ in range(rng.randrange(0, 301)))
+        s, pk = coracle.ed25519_sign(keys[i % 64], msg)
+        if i % 3 == 1 and msg:
+            msg = msg[:-1] + bytes([msg[-1] ^ 1])
+        if i % 3 == 2:
+            s = s[:40] + bytes([s[40] ^ 4]) + s[41:]
+        sigs.append(s), msgs.append(msg), pks.append(pk)
+    for strict in (False, True):
+        exp = coracle.ecverify_ed25519_msgs(sigs, msgs, pks, strict)
+        got = sigops.ed25519_eddsa.ecverify_msgs(sigs, msgs, pks, strict=strict)
+        assert (got == exp).all() and 0 < int(exp.sum()) < n

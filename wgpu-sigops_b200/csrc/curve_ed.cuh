@@ -59,17 +59,15 @@ SG_HD u64 sha512_k(int i) {
 
 SG_HD u64 rotr64(u64 x, int n) { return (x >> n) | (x << (64 - n)); }
 
-// in_w: 24 little-endian-loaded 32-bit words of the 96 message bytes.  out: 64 digest bytes as 16 LE-loaded words.
-SG_HD void sha512_96(u32* out_w, const u32* in_w) {
-    u64 w[16];
-#pragma unroll
-    for (int i = 0; i < 12; i++) w[i] = ((u64)bswap32(in_w[2 * i]) << 32) | bswap32(in_w[2 * i + 1]);
-    w[12] = 0x8000000000000000ull;
-    w[13] = 0;
-    w[14] = 0;
-    w[15] = 768;  // message length in bits
-    u64 a = 0x6a09e667f3bcc908ull, b = 0xbb67ae8584caa73bull, c = 0x3c6ef372fe94f82bull, d = 0xa54ff53a5f1d36f1ull;
-    u64 e = 0x510e527fade682d1ull, f = 0x9b05688c2b3e6c1full, g = 0x1f83d9abfb41bd6bull, h = 0x5be0cd19137e2179ull;
+#define SG_SHA512_IV                                                                                          \
+    {                                                                                                         \
+        0x6a09e667f3bcc908ull, 0xbb67ae8584caa73bull, 0x3c6ef372fe94f82bull, 0xa54ff53a5f1d36f1ull,           \
+            0x510e527fade682d1ull, 0x9b05688c2b3e6c1full, 0x1f83d9abfb41bd6bull, 0x5be0cd19137e2179ull        \
+    }
+
+// one compression: st += F(st, w); w is consumed (rolling 16-word schedule)
+SG_HD void sha512_compress(u64* st, u64* w) {
+    u64 a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll 1
     for (int t0 = 0; t0 < 80; t0 += 16) {
 #pragma unroll
@@ -96,14 +94,71 @@ SG_HD void sha512_96(u32* out_w, const u32* in_w) {
             a = t1 + t2;
         }
     }
-    u64 hh[8] = {a + 0x6a09e667f3bcc908ull, b + 0xbb67ae8584caa73bull, c + 0x3c6ef372fe94f82bull,
-                 d + 0xa54ff53a5f1d36f1ull, e + 0x510e527fade682d1ull, f + 0x9b05688c2b3e6c1full,
-                 g + 0x1f83d9abfb41bd6bull, h + 0x5be0cd19137e2179ull};
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
+SG_HD void sha512_digest_words(u32* out_w, const u64* st) {
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        out_w[2 * i] = bswap32((u32)(hh[i] >> 32));
-        out_w[2 * i + 1] = bswap32((u32)hh[i]);
+        out_w[2 * i] = bswap32((u32)(st[i] >> 32));
+        out_w[2 * i + 1] = bswap32((u32)st[i]);
     }
+}
+
+// in_w: 24 little-endian-loaded 32-bit words of the 96 message bytes.  out: 64 digest bytes as 16 LE-loaded words.
+SG_HD void sha512_96(u32* out_w, const u32* in_w) {
+    u64 w[16];
+#pragma unroll
+    for (int i = 0; i < 12; i++) w[i] = ((u64)bswap32(in_w[2 * i]) << 32) | bswap32(in_w[2 * i + 1]);
+    w[12] = 0x8000000000000000ull;
+    w[13] = 0;
+    w[14] = 0;
+    w[15] = 768;  // message length in bits
+    u64 st[8] = SG_SHA512_IV;
+    sha512_compress(st, w);
+    sha512_digest_words(out_w, st);
+}
+
+// SHA-512(R || A || M) for a message of any length read bytewise from memory (fuel_crypto::ed25519::verify takes
+// arbitrary-length messages; the reference hard-wires 32 bytes, src/wgsl/sha512.wgsl:114-123).
+SG_HD void sha512_ram(u32* out_w, const u32* r_w, const u32* a_w, const uint8_t* msg, size_t len) {
+    u64 st[8] = SG_SHA512_IV;
+    u64 w[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        w[i] = ((u64)bswap32(r_w[2 * i]) << 32) | bswap32(r_w[2 * i + 1]);
+        w[4 + i] = ((u64)bswap32(a_w[2 * i]) << 32) | bswap32(a_w[2 * i + 1]);
+    }
+#pragma unroll
+    for (int i = 8; i < 16; i++) w[i] = 0;
+    const size_t total = 64 + len;
+    size_t pos = 64;  // bytes placed so far (stream position)
+    size_t mi = 0;
+    bool pad_done = false, len_done = false;
+    while (!len_done) {
+        // fill the current block from byte (pos % 128) on
+        int idx = (int)(pos & 127);
+        while (idx < 128 && mi < len) {
+            w[idx >> 3] |= (u64)msg[mi] << (56 - 8 * (idx & 7));
+            idx++;
+            mi++;
+        }
+        pos = (pos & ~(size_t)127) + (size_t)idx;
+        if (idx < 128 && !pad_done) {
+            w[idx >> 3] |= (u64)0x80 << (56 - 8 * (idx & 7));
+            idx++;
+            pad_done = true;
+        }
+        if (pad_done && idx <= 112) {
+            w[15] |= (u64)total << 3;  // length in bits (total < 2^61)
+            len_done = true;
+        }
+        sha512_compress(st, w);
+#pragma unroll
+        for (int i = 0; i < 16; i++) w[i] = 0;
+        pos = (pos + 127) & ~(size_t)127;
+    }
+    sha512_digest_words(out_w, st);
 }
 
 // k = (512-bit little-endian integer h) mod L.  h = lo + hi*2^256 = mont(lo, R^2)... two Montgomery products:
@@ -316,20 +371,12 @@ SG_HD bool ed_sqrt_ratio_i(Fe& r, const Fe& u, const Fe& v) {
     return correct || flipped;
 }
 
-// One signature: sig_w 16 words (R || s), msg_w 8 words, pk_w 8 words (all little-endian-loaded bytes).
-// Returns 1 when the signature verifies, else 0.
-template <bool kSync>
-SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, const TabRef& tab, const u32* btab) {
-    typedef Sc<ModEdL> S;
-#if !defined(SG_NO_HOT_INLINE)
-    typedef Inl<Fp25519> FH;  // products inlined: one doubling, one cached-addition and one Niels-addition site
-#else
-    typedef Fp25519 FH;
-#endif
-    // A = decompress(pk): y from the low 255 bits (not checked against p), sign bit = bit 255
-    Fe y, yy, u, v, x, one;
-    u32 sign = pk_w[7] >> 31;
-    copy8(y.v, pk_w);
+// curve25519-dalek CompressedEdwardsY::decompress: y from the low 255 bits (no canonicity check), x from sqrt_ratio_i
+// with the sign bit applied.  Returns false when the encoding is not a curve point (x, y are then meaningless).
+SG_HD bool ed_decompress_xy(Fe& x, Fe& y, const u32* enc_w) {
+    Fe yy, u, v, one;
+    const u32 sign = enc_w[7] >> 31;
+    copy8(y.v, enc_w);
     y.v[7] &= 0x7FFFFFFFu;
     const Fe dconst = {SG_ED_D};
     FE::set_one(one);
@@ -337,24 +384,50 @@ SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, con
     FE::sub(u, yy, one);
     FE::mul(v, yy, dconst);
     FE::add(v, v, one);
+    const bool ok = ed_sqrt_ratio_i(x, u, v);
+    if (sign) FE::neg(x, x);
+    return ok;
+}
+
+// [8]P == identity  (dalek `is_small_order`)
+SG_HD bool ed_is_small_order(const Fe& x, const Fe& y) {
+    EdPoint P;
+    P.X = x;
+    P.Y = y;
+    FE::set_one(P.Z);
+    FE::set_zero(P.T);  // T is not read by the doubling
+#pragma unroll 1
+    for (int i = 0; i < 3; i++) ed_dbl<FE>(P, false);
+    return FE::is_zero(P.X) && FE::eq(P.Y, P.Z);
+}
+
+// One signature given the challenge digest dig = SHA-512(R || A || M) (16 LE-loaded words).
+// sig_w 16 words (R || s), pk_w 8 words.  kStrict adds dalek's `verify_strict` conditions: R must decompress and
+// neither A nor R may have small order.  Returns 1 when the signature verifies, else 0.
+template <bool kSync, bool kStrict>
+SG_HD u32 ed_verify_core(const u32* sig_w, const u32* pk_w, const u32* dig, const TabRef& tab, const u32* btab) {
+    typedef Sc<ModEdL> S;
+#if !defined(SG_NO_HOT_INLINE)
+    typedef Inl<Fp25519> FH;  // products inlined: one doubling, one cached-addition and one Niels-addition site
+#else
+    typedef Fp25519 FH;
+#endif
     phase_sync<kSync>();
     // No early exit (every thread of the block must reach every phase barrier): a key that does not decompress or a
     // non-canonical s keeps walking the program on whatever values it has and the verdict is forced to 0 at the end.
-    bool ok = ed_sqrt_ratio_i(x, u, v);
-    // -A: negate x exactly when the sign bit is clear (x from sqrt_ratio_i is the nonnegative root)
-    if (!sign) FE::neg(x, x);
+    Fe x, y;
+    bool ok = ed_decompress_xy(x, y, pk_w);
+    if (kStrict) {
+        Fe rx, ry;
+        ok = ed_decompress_xy(rx, ry, sig_w) && ok;
+        ok = ok && !ed_is_small_order(rx, ry) && !ed_is_small_order(x, y);
+    }
+    // -A
+    FE::neg(x, x);
     // canonical-scalar check on s
     ok = ok && S::lt_mod(sig_w + 8);
     phase_sync<kSync>();
-    // k = SHA-512(R || A || M) mod L
-    u32 pre[24], dig[16], k[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        pre[i] = sig_w[i];
-        pre[8 + i] = pk_w[i];
-        pre[16 + i] = msg_w[i];
-    }
-    sha512_96(dig, pre);
+    u32 k[8];
     ed_reduce512(k, dig);
     // table {1..8} * (-A), cached form
     phase_sync<kSync>();
@@ -427,6 +500,30 @@ SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, con
     FE::to_plain(enc, ay);
     enc[7] |= (FE::is_negative(ax) ? 1u : 0u) << 31;
     return (ok && eq8(enc, sig_w)) ? 1u : 0u;
+}
+
+// The reference's fixed-size case: 32-byte message, non-strict (src/ed25519_eddsa.rs:67-73).
+template <bool kSync>
+SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, const TabRef& tab, const u32* btab) {
+    u32 pre[24], dig[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        pre[i] = sig_w[i];
+        pre[8 + i] = pk_w[i];
+        pre[16 + i] = msg_w[i];
+    }
+    sha512_96(dig, pre);
+    return ed_verify_core<kSync, false>(sig_w, pk_w, dig, tab, btab);
+}
+
+// Variable-length message, optionally strict (fuel_crypto::ed25519::verify = dalek `verify_strict`).
+template <bool kSync>
+SG_HD u32 ed_verify_msg(const u32* sig_w, const uint8_t* msg, size_t len, const u32* pk_w, bool strict, const TabRef& tab,
+                        const u32* btab) {
+    u32 dig[16];
+    sha512_ram(dig, sig_w, pk_w, msg, len);
+    return strict ? ed_verify_core<kSync, true>(sig_w, pk_w, dig, tab, btab)
+                  : ed_verify_core<kSync, false>(sig_w, pk_w, dig, tab, btab);
 }
 
 }  // namespace sigops

@@ -125,6 +125,46 @@ __global__ void __launch_bounds__(kBlock, SG_MINB_ED) ed25519_verify_kernel(cons
     }
 }
 
+// ed25519 with variable-length messages and optional strict semantics (what
+// fuel_crypto::ed25519::verify needs; the reference hard-wires 32-byte messages, src/wgsl/sha512.wgsl:114-123).
+// msg_bytes: all messages back to back; msg_off[i] .. msg_off[i+1] delimit message i (n + 1 offsets).
+__global__ void __launch_bounds__(kBlock, SG_MINB_ED) ed25519_verify_msgs_kernel(
+    const Q4* __restrict__ sigs, const uint8_t* __restrict__ msg_bytes, const unsigned long long* __restrict__ msg_off,
+    const Q4* __restrict__ pks, size_t n, int strict, uint8_t* __restrict__ valid, Q4* __restrict__ scratch,
+    const u32* __restrict__ btab) {
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TabRef tab;
+    tab.base = scratch + gid;
+    tab.stride = (u32)nthreads;
+    for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += nthreads) {
+        phase_sync<true>();
+        size_t i = base + threadIdx.x;
+        const bool live = i < n;
+        if (!live) i = n - 1;
+        u32 sig_w[16], pk_w[8];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            Q4 v = sigs[4 * i + q];
+            sig_w[4 * q + 0] = v.x;
+            sig_w[4 * q + 1] = v.y;
+            sig_w[4 * q + 2] = v.z;
+            sig_w[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            Q4 p = pks[2 * i + q];
+            pk_w[4 * q + 0] = p.x;
+            pk_w[4 * q + 1] = p.y;
+            pk_w[4 * q + 2] = p.z;
+            pk_w[4 * q + 3] = p.w;
+        }
+        const unsigned long long lo = msg_off[i], hi = msg_off[i + 1];
+        const u32 v = ed_verify_msg<kInnerSync>(sig_w, msg_bytes + lo, (size_t)(hi - lo), pk_w, strict != 0, tab, btab);
+        if (live) valid[i] = (uint8_t)v;
+    }
+}
+
 // Fixed-base tables, generated once per device at init: thread j writes entry j (the (j+1)-th multiple) of
 //   k1tab  [2][kGTabEntries][16]  j*G and lambda*j*G        r1tab [kGTabEntries][16]  j*G (Montgomery form)
 //   edtab  [kGTabEntries][24]     j*B as affine Niels triples

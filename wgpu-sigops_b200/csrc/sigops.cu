@@ -60,7 +60,7 @@ struct Device {
     Q4* scratch = nullptr;
     size_t scratch_cap = 0;  // in Q4
     const u32 *k1g = nullptr, *r1g = nullptr, *edb = nullptr;
-    int grid_k1 = 0, grid_r1 = 0, grid_ed = 0, grid_unit = 0;
+    int grid_k1 = 0, grid_r1 = 0, grid_ed = 0, grid_edm = 0, grid_unit = 0;
     float ms_h2d = 0, ms_kernel = 0, ms_d2h = 0;
 };
 
@@ -131,6 +131,7 @@ int init_device(Device& d, int id) {
     if (max_grid(d, ecrecover_kernel<CurveK1>, &d.grid_k1)) return 1;
     if (max_grid(d, ecrecover_kernel<CurveR1>, &d.grid_r1)) return 1;
     if (max_grid(d, ed25519_verify_kernel, &d.grid_ed)) return 1;
+    if (max_grid(d, ed25519_verify_msgs_kernel, &d.grid_edm)) return 1;
     if (max_grid(d, unit_kernel, &d.grid_unit)) return 1;
     return 0;
 }
@@ -475,6 +476,92 @@ int sigops_secp256r1_ecrecover(const uint8_t* sigs, const uint8_t* msgs, size_t 
 int sigops_ed25519_ecverify(const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n,
                             uint8_t* out_valid) {
     return run_batch(OP_ED, sigs, msgs, pks, n, out_valid, nullptr);
+}
+
+// Variable-length-message ed25519: one device shard = signatures [lo, hi) and the message bytes they span.  No piecewise
+// pipeline here (one upload, one kernel, one download per shard).
+static int run_ed_msgs_shard(Device& d, const uint8_t* sigs, const uint8_t* msg_bytes, const uint64_t* off, const uint8_t* pks,
+                             size_t n, uint32_t flags, uint8_t* out) {
+    CK(cudaSetDevice(d.id));
+    const uint64_t b0 = off[0], nbytes = off[n] - off[0];
+    // layout: sigs | pks | offsets (n+1, rebased to 0) | message bytes
+    const size_t off_bytes = (n + 1) * sizeof(uint64_t);
+    const size_t in_bytes = n * 96 + off_bytes + (size_t)nbytes + 64;
+    if (ensure_buf(&d.d_in, &d.in_cap, in_bytes)) return 1;
+    if (ensure_buf(&d.d_out, &d.out_cap, n + 64)) return 1;
+    uint8_t* d_sigs = d.d_in;
+    uint8_t* d_pks = d.d_in + n * 64;
+    uint8_t* d_off = d.d_in + n * 96;
+    uint8_t* d_msg = d_off + off_bytes;
+    std::vector<uint64_t> rebased(n + 1);
+    for (size_t i = 0; i <= n; i++) {
+        if (off[i] < b0 || (i && off[i] < off[i - 1])) {
+            set_err("sigops_ed25519_ecverify_msgs: msg_offsets must be non-decreasing");
+            return 1;
+        }
+        rebased[i] = off[i] - b0;
+    }
+    CK(cudaEventRecord(d.ev[0], d.stream));
+    CK(cudaMemcpyAsync(d_sigs, sigs, n * 64, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(d_pks, pks, n * 32, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(d_off, rebased.data(), off_bytes, cudaMemcpyHostToDevice, d.stream));
+    if (nbytes) CK(cudaMemcpyAsync(d_msg, msg_bytes + b0, (size_t)nbytes, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaEventRecord(d.ev[1], d.stream));
+    int tpb = kBlock;
+    if (n < (size_t)d.sms * kBlock) {
+        size_t per_sm = (n + d.sms - 1) / d.sms;
+        tpb = (int)std::min<size_t>(kBlock, std::max<size_t>(32, (per_sm + 31) / 32 * 32));
+    }
+    int grid = (int)std::min<size_t>((n + tpb - 1) / tpb, (size_t)d.grid_edm);
+    if (ensure_scratch(d, (size_t)kEdTabChunks * d.grid_edm * kBlock)) return 1;
+    ed25519_verify_msgs_kernel<<<grid, tpb, 0, d.stream>>>((const Q4*)d_sigs, d_msg, (const unsigned long long*)d_off,
+                                                           (const Q4*)d_pks, n, (int)(flags & SIGOPS_ED25519_STRICT),
+                                                           d.d_out, d.scratch, d.edb);
+    CK(cudaGetLastError());
+    g_launches++;
+    CK(cudaEventRecord(d.ev[2], d.stream));
+    CK(cudaMemcpyAsync(out, d.d_out, n, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaEventRecord(d.ev[3], d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    CK(cudaEventElapsedTime(&d.ms_h2d, d.ev[0], d.ev[1]));
+    CK(cudaEventElapsedTime(&d.ms_kernel, d.ev[1], d.ev[2]));
+    CK(cudaEventElapsedTime(&d.ms_d2h, d.ev[2], d.ev[3]));
+    return 0;
+}
+
+int sigops_ed25519_ecverify_msgs(const uint8_t* sigs, const uint8_t* msg_bytes, const uint64_t* msg_offsets,
+                                 const uint8_t* pks, size_t n, uint32_t flags, uint8_t* out_valid) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (n == 0) return 0;
+    if (!sigs || !msg_offsets || !pks || !out_valid || (!msg_bytes && msg_offsets[n] != msg_offsets[0])) {
+        set_err("null buffer");
+        return 1;
+    }
+    if (int rc = do_init(nullptr, 0)) return rc;
+    for (auto& d : g_dev) d.ms_h2d = d.ms_kernel = d.ms_d2h = 0;
+    std::vector<size_t> bounds(g_dev.size() + 1);
+    const size_t G = (size_t)plan_shards(n, (int)g_dev.size(), bounds.data());
+    std::vector<int> rcs(G, 0);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; g++) {
+        const size_t lo = bounds[g], hi = bounds[g + 1];
+        auto work = [&, g, lo, hi]() {
+            // sub-shards bound the device buffers as in run_shard_bounded
+            for (size_t a = lo; a < hi && !rcs[g]; a += kMaxSubShard) {
+                const size_t m = std::min(kMaxSubShard, hi - a);
+                rcs[g] = run_ed_msgs_shard(g_dev[g], sigs + a * 64, msg_bytes, msg_offsets + a, pks + a * 32, m, flags,
+                                           out_valid + a);
+            }
+        };
+        if (G == 1)
+            work();
+        else
+            th.emplace_back(work);
+    }
+    for (auto& t : th) t.join();
+    for (size_t g = 0; g < G; g++)
+        if (rcs[g]) return rcs[g];
+    return 0;
 }
 
 int sigops_secp256k1_ecrecover_device(const void* d_sigs, const void* d_msgs, size_t n, void* d_out, void* d_status,
