@@ -79,6 +79,19 @@ int sigops_ed25519_ecverify(const uint8_t* sigs, const uint8_t* msgs, const uint
 int sigops_ed25519_ecverify_msgs(const uint8_t* sigs, const uint8_t* msg_bytes, const uint64_t* msg_offsets,
                                  const uint8_t* pks, size_t n, uint32_t flags, uint8_t* out_valid);
 
+/* The steps on either side of recovery, on the device.  The reference's callers hash every
+ * transaction to a `fuel_crypto::Message` (SHA-256) on the host before calling ecrecover
+ * (src/tests/secp256k1_ecdsa.rs:21-22, src/benchmarks/secp256k1_ecdsa.rs:160-165) and derive the Fuel address
+ * SHA-256(X || Y) from each returned key afterwards.
+ * sigops_sha256_batch: out[i] = SHA-256(data[offsets[i] .. offsets[i+1])), 32 bytes each.
+ * sigops_ecrecover_addresses: curve = SIGOPS_CURVE_SECP256K1 | SIGOPS_CURVE_SECP256R1.  msg_offsets != NULL: msg_bytes
+ * holds the raw messages back to back and each is hashed with SHA-256 first; msg_offsets == NULL: msg_bytes holds n
+ * 32-byte prehashes.  out_addresses: n * 32 bytes (zero where out_status[i] != 0); out_pubkeys (n * 64) and out_status
+ * (n) may be NULL. */
+int sigops_sha256_batch(const uint8_t* data, const uint64_t* offsets, size_t n, uint8_t* out);
+int sigops_ecrecover_addresses(int curve, const uint8_t* sigs, const uint8_t* msg_bytes, const uint64_t* msg_offsets,
+                               size_t n, uint8_t* out_addresses, uint8_t* out_pubkeys, uint8_t* out_status);
+
 /* precompute::{secp256k1_bases, secp256r1_bases, ed25519_bases}  (src/precompute.rs:12,36-69).
  * CPU-only compatibility table: 16 multiples (i+1)*G, coordinates in Montgomery form with
  * R = 2^(num_limbs*log_limb_size), little-endian log_limb_size-bit limbs; x||y per entry for the secp curves
@@ -166,7 +179,8 @@ enum {
     SIGOPS_UNIT_K1_INV_FERMAT = 33,
     SIGOPS_UNIT_R1_INV_FERMAT = 34,
     SIGOPS_UNIT_ED_INV_FERMAT = 35,
-    SIGOPS_UNIT_COUNT = 36
+    SIGOPS_UNIT_SHA256_64 = 36,      /* in 16 (64 bytes)        out 8  : SHA-256 digest bytes           */
+    SIGOPS_UNIT_COUNT = 37
 };
 
 #ifdef __cplusplus

@@ -9,6 +9,9 @@ extern "C" {
     pub fn sigops_secp256k1_ecrecover(sigs: *const u8, msgs: *const u8, n: usize, out_pubkeys: *mut u8, out_status: *mut u8) -> c_int;
     pub fn sigops_secp256r1_ecrecover(sigs: *const u8, msgs: *const u8, n: usize, out_pubkeys: *mut u8, out_status: *mut u8) -> c_int;
     pub fn sigops_ed25519_ecverify(sigs: *const u8, msgs: *const u8, pks: *const u8, n: usize, out_valid: *mut u8) -> c_int;
+    pub fn sigops_ed25519_ecverify_msgs(sigs: *const u8, msg_bytes: *const u8, msg_offsets: *const u64, pks: *const u8, n: usize, flags: u32, out_valid: *mut u8) -> c_int;
+    pub fn sigops_sha256_batch(data: *const u8, offsets: *const u64, n: usize, out: *mut u8) -> c_int;
+    pub fn sigops_ecrecover_addresses(curve: c_int, sigs: *const u8, msg_bytes: *const u8, msg_offsets: *const u64, n: usize, out_addresses: *mut u8, out_pubkeys: *mut u8, out_status: *mut u8) -> c_int;
     pub fn sigops_precompute_bases(curve: c_int, log_limb_size: u32, out: *mut u32, inout_len: *mut usize) -> c_int;
     pub fn sigops_plan_shards(n: usize, n_devices: c_int, bounds: *mut usize, n_used: *mut c_int) -> c_int;
     pub fn sigops_last_timing(h2d_ms: *mut f64, kernel_ms: *mut f64, d2h_ms: *mut f64) -> c_int;

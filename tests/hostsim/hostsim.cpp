@@ -92,4 +92,13 @@ int hostsim_ed25519_verify_msgs(const uint8_t* sigs, const uint8_t* msg_bytes, c
     }
     return 0;
 }
+
+int hostsim_sha256(const uint8_t* data, const uint64_t* off, size_t n, uint8_t* out) {
+    for (size_t i = 0; i < n; i++) {
+        u32 d[8];
+        sha256_ram(d, data + off[i], (size_t)(off[i + 1] - off[i]));
+        memcpy(out + 32 * i, d, 32);
+    }
+    return 0;
+}
 }

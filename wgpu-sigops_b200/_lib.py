@@ -18,7 +18,7 @@ SYMBOLS = [
     "sigops_host_alloc", "sigops_host_free",
     "sigops_secp256k1_ecrecover_device", "sigops_secp256r1_ecrecover_device", "sigops_ed25519_ecverify_device",
     "sigops_test_unit", "sigops_test_unit_shape", "sigops_imad_peak", "sigops_plan_shards",
-    "sigops_ed25519_ecverify_msgs",
+    "sigops_ed25519_ecverify_msgs", "sigops_sha256_batch", "sigops_ecrecover_addresses",
 ]
 
 _lib = None
@@ -46,6 +46,8 @@ def load() -> ctypes.CDLL:
     lib.sigops_secp256r1_ecrecover.argtypes = [vp, vp, sz, vp, vp]
     lib.sigops_ed25519_ecverify.argtypes = [vp, vp, vp, sz, vp]
     lib.sigops_ed25519_ecverify_msgs.argtypes = [vp, vp, vp, vp, sz, c.c_uint32, vp]
+    lib.sigops_sha256_batch.argtypes = [vp, vp, sz, vp]
+    lib.sigops_ecrecover_addresses.argtypes = [i32, vp, vp, vp, sz, vp, vp, vp]
     lib.sigops_precompute_bases.argtypes = [i32, c.c_uint32, vp, c.POINTER(sz)]
     lib.sigops_last_timing.argtypes = [c.POINTER(c.c_double)] * 3
     lib.sigops_kernel_launches.restype = c.c_uint64

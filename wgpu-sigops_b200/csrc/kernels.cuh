@@ -9,6 +9,7 @@
 #pragma once
 #include "../../include/sigops.h"
 #include "curve_ed.cuh"
+#include "sha256.cuh"
 
 namespace sigops {
 
@@ -165,6 +166,32 @@ __global__ void __launch_bounds__(kBlock, SG_MINB_ED) ed25519_verify_msgs_kernel
     }
 }
 
+// SHA-256 of n variable-length messages (one per thread): the `Message::new` prehash done on the device.
+__global__ void __launch_bounds__(256) sha256_msgs_kernel(const uint8_t* __restrict__ bytes,
+                                                          const unsigned long long* __restrict__ off, size_t n,
+                                                          u32* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 d[8];
+    sha256_ram(d, bytes + off[i], (size_t)(off[i + 1] - off[i]));
+#pragma unroll
+    for (int j = 0; j < 8; j++) out[i * 8 + j] = d[j];
+}
+
+// Fuel address of each recovered key: SHA-256(X || Y); 32 zero bytes where the recovery was rejected.
+__global__ void __launch_bounds__(256) sha256_pubkeys_kernel(const u32* __restrict__ pubkeys, const uint8_t* __restrict__ status,
+                                                             size_t n, u32* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 in[16], d[8];
+#pragma unroll
+    for (int j = 0; j < 16; j++) in[j] = pubkeys[i * 16 + j];
+    sha256_64(d, in);
+    const bool bad = status && status[i] != 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) out[i * 8 + j] = bad ? 0u : d[j];
+}
+
 // Fixed-base tables, generated once per device at init: thread j writes entry j (the (j+1)-th multiple) of
 //   k1tab  [2][kGTabEntries][16]  j*G and lambda*j*G        r1tab [kGTabEntries][16]  j*G (Montgomery form)
 //   edtab  [kGTabEntries][24]     j*B as affine Niels triples
@@ -205,6 +232,10 @@ SG_HD void unit_shape(int op, int& in_w, int& out_w) {
         case SIGOPS_UNIT_SHA512_96:
             in_w = 24;
             out_w = 16;
+            break;
+        case SIGOPS_UNIT_SHA256_64:
+            in_w = 16;
+            out_w = 8;
             break;
         case SIGOPS_UNIT_K1_GLV:
             out_w = 12;
@@ -358,6 +389,9 @@ SG_HD void unit_dispatch(int op, u32* out, const u32* in, const TabRef& tab, con
             break;
         case SIGOPS_UNIT_SHA512_96:
             sha512_96(out, in);
+            break;
+        case SIGOPS_UNIT_SHA256_64:
+            sha256_64(out, in);
             break;
         case SIGOPS_UNIT_K1_GLV: {
             GlvSplit s;

@@ -564,6 +564,138 @@ int sigops_ed25519_ecverify_msgs(const uint8_t* sigs, const uint8_t* msg_bytes, 
     return 0;
 }
 
+// raw messages -> SHA-256 -> recover -> SHA-256(pubkey), all on the device; one shard, one stream, no host pass
+static int run_addresses_shard(Device& d, Op op, const uint8_t* sigs, const uint8_t* msg_bytes, const uint64_t* off, size_t n,
+                               uint8_t* out_addr, uint8_t* out_pk, uint8_t* out_st) {
+    CK(cudaSetDevice(d.id));
+    const uint64_t b0 = off ? off[0] : 0, nbytes = off ? off[n] - off[0] : (uint64_t)n * 32;
+    const size_t off_bytes = off ? (n + 1) * sizeof(uint64_t) : 0;
+    // d_in: sigs | prehashes (n*32) | offsets | raw bytes        d_out: pubkeys (n*64) | status (n) | pad | addresses
+    const size_t in_bytes = n * 96 + off_bytes + (off ? (size_t)nbytes : 0) + 64;
+    const size_t addr_off = (n * 65 + 63) / 64 * 64;
+    if (ensure_buf(&d.d_in, &d.in_cap, in_bytes)) return 1;
+    if (ensure_buf(&d.d_out, &d.out_cap, addr_off + n * 32 + 64)) return 1;
+    uint8_t* d_sigs = d.d_in;
+    uint8_t* d_msgs = d.d_in + n * 64;
+    uint8_t* d_off = d.d_in + n * 96;
+    uint8_t* d_raw = d_off + off_bytes;
+    uint8_t* d_status = d.d_out + n * 64;
+    uint8_t* d_addr = d.d_out + addr_off;
+    CK(cudaEventRecord(d.ev[0], d.stream));
+    CK(cudaMemcpyAsync(d_sigs, sigs, n * 64, cudaMemcpyHostToDevice, d.stream));
+    if (off) {
+        std::vector<uint64_t> rebased(n + 1);
+        for (size_t i = 0; i <= n; i++) {
+            if (off[i] < b0 || (i && off[i] < off[i - 1])) {
+                set_err("sigops_ecrecover_addresses: msg_offsets must be non-decreasing");
+                return 1;
+            }
+            rebased[i] = off[i] - b0;
+        }
+        CK(cudaMemcpyAsync(d_off, rebased.data(), off_bytes, cudaMemcpyHostToDevice, d.stream));
+        if (nbytes) CK(cudaMemcpyAsync(d_raw, msg_bytes + b0, (size_t)nbytes, cudaMemcpyHostToDevice, d.stream));
+        CK(cudaStreamSynchronize(d.stream));  // `rebased` is pageable and goes out of scope
+        CK(cudaEventRecord(d.ev[1], d.stream));
+        sha256_msgs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(d_raw, (const unsigned long long*)d_off, n,
+                                                                             (u32*)d_msgs);
+        CK(cudaGetLastError());
+        g_launches++;
+    } else {
+        CK(cudaMemcpyAsync(d_msgs, msg_bytes, n * 32, cudaMemcpyHostToDevice, d.stream));
+        CK(cudaEventRecord(d.ev[1], d.stream));
+    }
+    if (launch_op(d, op, d_sigs, d_msgs, nullptr, n, d.d_out, d_status, d.stream)) return 1;
+    sha256_pubkeys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>((const u32*)d.d_out, d_status, n, (u32*)d_addr);
+    CK(cudaGetLastError());
+    g_launches++;
+    CK(cudaEventRecord(d.ev[2], d.stream));
+    CK(cudaMemcpyAsync(out_addr, d_addr, n * 32, cudaMemcpyDeviceToHost, d.stream));
+    if (out_pk) CK(cudaMemcpyAsync(out_pk, d.d_out, n * 64, cudaMemcpyDeviceToHost, d.stream));
+    if (out_st) CK(cudaMemcpyAsync(out_st, d_status, n, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaEventRecord(d.ev[3], d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    CK(cudaEventElapsedTime(&d.ms_h2d, d.ev[0], d.ev[1]));
+    CK(cudaEventElapsedTime(&d.ms_kernel, d.ev[1], d.ev[2]));
+    CK(cudaEventElapsedTime(&d.ms_d2h, d.ev[2], d.ev[3]));
+    return 0;
+}
+
+int sigops_ecrecover_addresses(int curve, const uint8_t* sigs, const uint8_t* msg_bytes, const uint64_t* msg_offsets,
+                               size_t n, uint8_t* out_addresses, uint8_t* out_pubkeys, uint8_t* out_status) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (n == 0) return 0;
+    if (curve != SIGOPS_CURVE_SECP256K1 && curve != SIGOPS_CURVE_SECP256R1) {
+        set_err("sigops_ecrecover_addresses: curve must be secp256k1 or secp256r1");
+        return 1;
+    }
+    if (!sigs || !out_addresses || (!msg_bytes && (!msg_offsets || msg_offsets[n] != msg_offsets[0]))) {
+        set_err("null buffer");
+        return 1;
+    }
+    if (int rc = do_init(nullptr, 0)) return rc;
+    for (auto& d : g_dev) d.ms_h2d = d.ms_kernel = d.ms_d2h = 0;
+    const Op op = curve == SIGOPS_CURVE_SECP256K1 ? OP_K1 : OP_R1;
+    std::vector<size_t> bounds(g_dev.size() + 1);
+    const size_t G = (size_t)plan_shards(n, (int)g_dev.size(), bounds.data());
+    std::vector<int> rcs(G, 0);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; g++) {
+        const size_t lo = bounds[g], hi = bounds[g + 1];
+        auto work = [&, g, lo, hi]() {
+            for (size_t a = lo; a < hi && !rcs[g]; a += kMaxSubShard) {
+                const size_t m = std::min(kMaxSubShard, hi - a);
+                rcs[g] = run_addresses_shard(g_dev[g], op, sigs + a * 64, msg_offsets ? msg_bytes : msg_bytes + a * 32,
+                                             msg_offsets ? msg_offsets + a : nullptr, m, out_addresses + a * 32,
+                                             out_pubkeys ? out_pubkeys + a * 64 : nullptr, out_status ? out_status + a : nullptr);
+            }
+        };
+        if (G == 1)
+            work();
+        else
+            th.emplace_back(work);
+    }
+    for (auto& t : th) t.join();
+    for (size_t g = 0; g < G; g++)
+        if (rcs[g]) return rcs[g];
+    return 0;
+}
+
+int sigops_sha256_batch(const uint8_t* data, const uint64_t* offsets, size_t n, uint8_t* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (n == 0) return 0;
+    if (!offsets || !out || (!data && offsets[n] != offsets[0])) {
+        set_err("null buffer");
+        return 1;
+    }
+    if (int rc = do_init(nullptr, 0)) return rc;
+    Device& d = g_dev[0];
+    CK(cudaSetDevice(d.id));
+    for (size_t a = 0; a < n; a += kMaxSubShard) {
+        const size_t m = std::min(kMaxSubShard, n - a);
+        const uint64_t b0 = offsets[a], nbytes = offsets[a + m] - b0;
+        const size_t off_bytes = (m + 1) * sizeof(uint64_t);
+        if (ensure_buf(&d.d_in, &d.in_cap, off_bytes + (size_t)nbytes + 64)) return 1;
+        if (ensure_buf(&d.d_out, &d.out_cap, m * 32 + 64)) return 1;
+        std::vector<uint64_t> rebased(m + 1);
+        for (size_t i = 0; i <= m; i++) {
+            if (offsets[a + i] < b0 || (i && offsets[a + i] < offsets[a + i - 1])) {
+                set_err("sigops_sha256_batch: offsets must be non-decreasing");
+                return 1;
+            }
+            rebased[i] = offsets[a + i] - b0;
+        }
+        CK(cudaMemcpyAsync(d.d_in, rebased.data(), off_bytes, cudaMemcpyHostToDevice, d.stream));
+        if (nbytes) CK(cudaMemcpyAsync(d.d_in + off_bytes, data + b0, (size_t)nbytes, cudaMemcpyHostToDevice, d.stream));
+        sha256_msgs_kernel<<<(unsigned)((m + 255) / 256), 256, 0, d.stream>>>(d.d_in + off_bytes,
+                                                                             (const unsigned long long*)d.d_in, m, (u32*)d.d_out);
+        CK(cudaGetLastError());
+        g_launches++;
+        CK(cudaMemcpyAsync(out + a * 32, d.d_out, m * 32, cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+    }
+    return 0;
+}
+
 int sigops_secp256k1_ecrecover_device(const void* d_sigs, const void* d_msgs, size_t n, void* d_out, void* d_status,
                                       void* stream) {
     return run_device(OP_K1, d_sigs, d_msgs, nullptr, n, d_out, d_status, stream);
