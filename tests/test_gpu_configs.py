@@ -86,3 +86,14 @@ def test_multi_device_sharding_matches_single(sigops):
     assert (out == pk).all() and (got == st).all()
     s, m, p, v, _ = batches.ed25519_batch(100003, edge_every=7, seed=22)
     assert (sigops.ed25519_eddsa.ecverify_array(s, m, p) == v).all()
+
+
+def test_sub_shards_cover_large_batches(sigops, monkeypatch):
+    """Batches beyond the device-buffer bound are processed in sub-shards (2^24 signatures in production; forced down
+    to 10,000 here): results identical to the single-pass ones, ragged last sub-shard included."""
+    s, m, pk, st, _ = batches.ecdsa_batch(0, 34567, edge_every=113, seed=41)
+    monkeypatch.setenv("SIGOPS_MAX_SUBSHARD", "10000")
+    out, got = sigops.secp256k1_ecdsa.ecrecover_with_status(s, m)
+    assert (out == pk).all() and (got == st).all()
+    s2, m2, p2, v, _ = batches.ed25519_batch(23456, edge_every=9, seed=42)
+    assert (sigops.ed25519_eddsa.ecverify_array(s2, m2, p2) == v).all()

@@ -292,8 +292,10 @@ int run_shard_bounded(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs
                       uint8_t* out, uint8_t* status) {
     const size_t out_stride = op == OP_ED ? 1 : 64;
     float h2d = 0, ker = 0, d2h = 0;
-    for (size_t lo = 0; lo < n; lo += kMaxSubShard) {
-        const size_t m = std::min(kMaxSubShard, n - lo);
+    size_t sub = kMaxSubShard;
+    if (const char* e = getenv("SIGOPS_MAX_SUBSHARD")) sub = std::max<size_t>(1, (size_t)atoll(e));  // test hook
+    for (size_t lo = 0; lo < n; lo += sub) {
+        const size_t m = std::min(sub, n - lo);
         if (int rc = run_shard(d, op, sigs + lo * 64, msgs + lo * 32, pks ? pks + lo * 32 : nullptr, m,
                                out + lo * out_stride, status ? status + lo : nullptr))
             return rc;
