@@ -4,6 +4,7 @@
 // are replaced by their portable uint64_t twins (arith.cuh, SG_PTX == 0).  This lets the `-m "not gpu"` tests check
 // all the host-visible logic -- reductions, addition chains, group law corner cases, recoding, GLV split, the
 // fused per-signature functions -- against the oracle without a GPU.  It is never linked into libsigops.so.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 #include "../../wgpu-sigops_b200/csrc/kernels.cuh"
@@ -48,32 +49,75 @@ int hostsim_unit_shape(int op, int* in_w, int* out_w) {
     return 0;
 }
 
-int hostsim_ecrecover(int curve, const uint8_t* sigs, const uint8_t* msgs, size_t n, uint8_t* out, uint8_t* status) {
-    ensure_tables();
-    std::vector<Q4> scratch(kSwTabChunks);
-    TabRef tab{scratch.data(), 1};
-    for (size_t i = 0; i < n; i++) {
-        u32 sig_w[16], msg_w[8], out_w[16];
+struct HostIO {
+    const uint8_t* sigs;
+    const uint8_t* msgs;
+    uint8_t* out;
+    uint8_t* status;
+    size_t n, first;
+    void load(int j, u32* sig_w, u32* msg_w) const {
+        size_t i = first + (size_t)j;
+        if (i >= n) i = n - 1;
         memcpy(sig_w, sigs + 64 * i, 64);
         memcpy(msg_w, msgs + 32 * i, 32);
-        u32 st = curve == 0 ? sw_ecrecover_one<CurveK1, false>(out_w, sig_w, msg_w, tab, k1_gtab.data())
-                            : sw_ecrecover_one<CurveR1, false>(out_w, sig_w, msg_w, tab, r1_gtab.data());
+    }
+    void store(int j, const u32* out_w, u32 st) const {
+        const size_t i = first + (size_t)j;
+        if (i >= n) return;
         memcpy(out + 64 * i, out_w, 64);
         if (status) status[i] = (uint8_t)st;
+    }
+};
+
+// batch = signatures per shared-inversion batch (1..kSwBatch), so the tests cover full, partial and single batches
+int hostsim_ecrecover(int curve, const uint8_t* sigs, const uint8_t* msgs, size_t n, uint8_t* out, uint8_t* status) {
+    ensure_tables();
+    std::vector<Q4> scratch(kSwBatchChunks);
+    TabRef tab{scratch.data(), 1};
+    HostIO io{sigs, msgs, out, status, n, 0};
+    int batch = kSwBatch;
+    for (size_t i = 0; i < n;) {
+        io.first = i;
+        const int B = (int)std::min<size_t>((size_t)batch, n - i);
+        i += (size_t)B;
+        if (curve == 0)
+            sw_ecrecover_batch<CurveK1, false>(B, io, tab, k1_gtab.data());
+        else
+            sw_ecrecover_batch<CurveR1, false>(B, io, tab, r1_gtab.data());
+        batch = batch == 1 ? kSwBatch : batch - 1;  // 8, 7, ..., 1, 8, ...: every batch size gets exercised
     }
     return 0;
 }
 
-int hostsim_ed25519_verify(const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n, uint8_t* valid) {
-    ensure_tables();
-    std::vector<Q4> scratch(kEdTabChunks);
-    TabRef tab{scratch.data(), 1};
-    for (size_t i = 0; i < n; i++) {
-        u32 sig_w[16], msg_w[8], pk_w[8];
+struct HostEdIO {
+    const uint8_t *sigs, *msgs, *pks;
+    uint8_t* valid;
+    size_t n, first;
+    void load(int j, u32* sig_w, u32* msg_w, u32* pk_w) const {
+        size_t i = first + (size_t)j;
+        if (i >= n) i = n - 1;
         memcpy(sig_w, sigs + 64 * i, 64);
         memcpy(msg_w, msgs + 32 * i, 32);
         memcpy(pk_w, pks + 32 * i, 32);
-        valid[i] = (uint8_t)ed_verify_one<false>(sig_w, msg_w, pk_w, tab, ed_btab.data());
+    }
+    void store(int j, u32 v) const {
+        const size_t i = first + (size_t)j;
+        if (i < n) valid[i] = (uint8_t)v;
+    }
+};
+
+int hostsim_ed25519_verify(const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n, uint8_t* valid) {
+    ensure_tables();
+    std::vector<Q4> scratch(kEdBatchChunks);
+    TabRef tab{scratch.data(), 1};
+    HostEdIO io{sigs, msgs, pks, valid, n, 0};
+    int batch = kEdBatch;
+    for (size_t i = 0; i < n;) {
+        io.first = i;
+        const int B = (int)std::min<size_t>((size_t)batch, n - i);
+        i += (size_t)B;
+        ed_verify_batch<false>(B, io, tab, ed_btab.data());
+        batch = batch == 1 ? kEdBatch : batch - 1;
     }
     return 0;
 }

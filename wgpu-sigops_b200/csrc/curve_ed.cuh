@@ -404,8 +404,9 @@ SG_HD bool ed_is_small_order(const Fe& x, const Fe& y) {
 // One signature given the challenge digest dig = SHA-512(R || A || M) (16 LE-loaded words).
 // sig_w 16 words (R || s), pk_w 8 words.  kStrict adds dalek's `verify_strict` conditions: R must decompress and
 // neither A nor R may have small order.  Returns 1 when the signature verifies, else 0.
+// Part 1: everything up to the projective point R' = [s]B + [k](-A).  Returns whether the inputs were acceptable so far.
 template <bool kSync, bool kStrict>
-SG_HD u32 ed_verify_core(const u32* sig_w, const u32* pk_w, const u32* dig, const TabRef& tab, const u32* btab) {
+SG_HD bool ed_verify_point(EdPoint& acc, const u32* sig_w, const u32* pk_w, const u32* dig, const TabRef& tab, const u32* btab) {
     typedef Sc<ModEdL> S;
 #if !defined(SG_NO_HOT_INLINE)
     typedef Inl<Fp25519> FH;  // products inlined: one doubling, one cached-addition and one Niels-addition site
@@ -472,7 +473,6 @@ SG_HD u32 ed_verify_core(const u32* sig_w, const u32* pk_w, const u32* dig, cons
     kp[1][8] = kp[1][9] = 0;
     recode_offset<8, 4, 64>(kp[0]);      // k < L < 2^253: k + C < 2^256
     recode_offset<9, kGWin, 22>(kp[1]);  // s < L: s + C < 2^264
-    EdPoint acc;
     ed_set_identity(acc);
     int gcount = 0;  // B windows sit on every third k window: i = 63, 60, ..., 0  <->  window i / 3
 #pragma unroll 1
@@ -490,16 +490,87 @@ SG_HD u32 ed_verify_core(const u32* sig_w, const u32* pk_w, const u32* dig, cons
             gcount--;
         }
     }
-    // compress and compare with the signature's R bytes
-    phase_sync<kSync>();
-    Fe zi, ax, ay;
-    fe_inv((FE*)0, zi, acc.Z);
+    // a key that is not a curve point can drive Z to zero: keep the inversion chain invertible (the verdict is 0 anyway)
+    if (!ok || FE::is_zero(acc.Z)) {
+        ok = false;
+        FE::set_one(acc.Z);
+    }
+    return ok;
+}
+
+// Part 2: compress R' with zi = Z^-1 and compare with the signature's R bytes
+SG_HD u32 ed_verify_finish(const EdPoint& acc, const Fe& zi, const u32* sig_w, bool ok) {
+    Fe ax, ay;
     FE::mul(ax, acc.X, zi);
     FE::mul(ay, acc.Y, zi);
     u32 enc[8];
     FE::to_plain(enc, ay);
     enc[7] |= (FE::is_negative(ax) ? 1u : 0u) << 31;
     return (ok && eq8(enc, sig_w)) ? 1u : 0u;
+}
+
+// One signature given the challenge digest (variable-length / strict entry point, unit shims)
+template <bool kSync, bool kStrict>
+SG_HD u32 ed_verify_core(const u32* sig_w, const u32* pk_w, const u32* dig, const TabRef& tab, const u32* btab) {
+    EdPoint acc;
+    const bool ok = ed_verify_point<kSync, kStrict>(acc, sig_w, pk_w, dig, tab, btab);
+    phase_sync<kSync>();
+    Fe zi;
+    fe_inv((FE*)0, zi, acc.Z);
+    return ed_verify_finish(acc, zi, sig_w, ok);
+}
+
+// Batched verification of the reference's fixed-size case (32-byte messages, non-strict): one thread walks B <= kEdBatch
+// signatures and pays the final inversion once (Montgomery's trick), as sw_ecrecover_batch does.
+// IO:  io.load(j, sig_w[16], msg_w[8], pk_w[8])  and  io.store(j, verdict).
+// Scratch in 16-byte chunks: the table {1..8}(-A) (kEdTabChunks, reused by every signature of the batch), then per
+// signature X, Y, Z (6) and the Z-chain slot (2).
+static constexpr int kEdBatch = 8;
+static constexpr int kEdBatchChunks = kEdTabChunks + 8 * kEdBatch;
+
+template <bool kSync, class IO>
+SG_HD void ed_verify_batch(int B, IO& io, const TabRef& scratch, const u32* btab) {
+    const int kQ = kEdTabChunks, kZP = kQ + 6 * kEdBatch;
+    u32 sig_w[16], msg_w[8], pk_w[8];
+    u32 good = 0;
+    Fe one, c, inv;
+    FE::set_one(one);
+    c = one;
+#pragma unroll 1
+    for (int j = 0; j < B; j++) {
+        phase_sync<kSync>();
+        io.load(j, sig_w, msg_w, pk_w);
+        u32 pre[24], dig[16];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            pre[i] = sig_w[i];
+            pre[8 + i] = pk_w[i];
+            pre[16 + i] = msg_w[i];
+        }
+        sha512_96(dig, pre);
+        EdPoint acc;
+        if (ed_verify_point<kSync, false>(acc, sig_w, pk_w, dig, scratch, btab)) good |= 1u << j;
+        tab_store_fe(scratch, kQ + 6 * j, acc.X);
+        tab_store_fe(scratch, kQ + 6 * j + 2, acc.Y);
+        tab_store_fe(scratch, kQ + 6 * j + 4, acc.Z);
+        FE::mul(c, c, acc.Z);
+        tab_store_fe(scratch, kZP + 2 * j, c);
+    }
+    phase_sync<kSync>();
+    fe_inv((FE*)0, inv, c);
+#pragma unroll 1
+    for (int j = B - 1; j >= 0; j--) {
+        EdPoint acc;
+        Fe zi, cp = one;
+        tab_load_fe(acc.X, scratch, kQ + 6 * j);
+        tab_load_fe(acc.Y, scratch, kQ + 6 * j + 2);
+        tab_load_fe(acc.Z, scratch, kQ + 6 * j + 4);
+        if (j > 0) tab_load_fe(cp, scratch, kZP + 2 * (j - 1));
+        FE::mul(zi, inv, cp);
+        FE::mul(inv, inv, acc.Z);
+        io.load(j, sig_w, msg_w, pk_w);
+        io.store(j, ed_verify_finish(acc, zi, sig_w, ((good >> j) & 1u) != 0));
+    }
 }
 
 // The reference's fixed-size case: 32-byte message, non-strict (src/ed25519_eddsa.rs:67-73).

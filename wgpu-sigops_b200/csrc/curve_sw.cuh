@@ -265,12 +265,14 @@ static constexpr int kSwTabZ = 32, kSwTabC = 46;
 static constexpr int kGWin = 12;
 static constexpr int kGTabEntries = 1 << (kGWin - 1);
 
+// Step 1 of the table: the Jacobian multiples 2R..8R (X, Y parked in their final slots, Z in the temp area) and the
+// running product of their Z (prefix products stored per entry).  `c` is the running product on entry and exit, so the
+// chain can span several signatures' tables (one shared inversion for all of them).
 template <class C>
-SG_HD void sw_build_table(const TabRef& tab, const Fe& x, const Fe& y) {
+SG_HD void sw_table_park(const TabRef& tab, const Fe& x, const Fe& y, Fe& c) {
     typedef typename C::F F;
     tab_store_fe(tab, 0, x);
     tab_store_fe(tab, 2, y);
-    // Jacobian multiples 2R..8R: X, Y parked in their final slots, Z in the temp area
     {
         JacPoint P1, P2, P3, P4, T;
         P1.X = x;
@@ -303,30 +305,32 @@ SG_HD void sw_build_table(const TabRef& tab, const Fe& x, const Fe& y) {
         SG_PARK(7, T);  // 8R
 #undef SG_PARK
     }
-    // prefix products c_j = Z_2 * ... * Z_j  (R has prime order n > 8: no multiple is infinity, every Z_j != 0)
-    Fe c, z;
-    tab_load_fe(c, tab, kSwTabZ);
-    tab_store_fe(tab, kSwTabC, c);
+    // prefix products (R has prime order n > 8: no multiple is infinity, every Z_j != 0)
+    Fe z;
 #pragma unroll 1
-    for (int j = 3; j <= 8; j++) {
+    for (int j = 2; j <= 8; j++) {
         tab_load_fe(z, tab, kSwTabZ + 2 * (j - 2));
         F::mul(c, c, z);
         tab_store_fe(tab, kSwTabC + 2 * (j - 2), c);
     }
-    Fe inv;
-    fe_inv((F*)0, inv, c);
-    // walk back: zinv_j = inv * c_(j-1), inv <- inv * Z_j; then x = X / Z^2, y = Y / Z^3
+}
+
+// Step 2: given inv = (running product after this table)^-1 and c_before = the running product before this table, walk
+// the table back: zinv_j = inv * c_(j-1), inv <- inv * Z_j; x = X / Z^2, y = Y / Z^3.  On exit inv = c_before^-1.
+template <class C>
+SG_HD void sw_table_normalize(const TabRef& tab, Fe& inv, const Fe& c_before) {
+    typedef typename C::F F;
+    Fe z;
 #pragma unroll 1
     for (int j = 8; j >= 2; j--) {
         Fe zi, zi2, t;
-        if (j > 2) {
+        if (j > 2)
             tab_load_fe(t, tab, kSwTabC + 2 * (j - 3));
-            F::mul(zi, inv, t);
-            tab_load_fe(z, tab, kSwTabZ + 2 * (j - 2));
-            F::mul(inv, inv, z);
-        } else {
-            zi = inv;
-        }
+        else
+            t = c_before;
+        F::mul(zi, inv, t);
+        tab_load_fe(z, tab, kSwTabZ + 2 * (j - 2));
+        F::mul(inv, inv, z);
         F::sqr(zi2, zi);
         tab_load_fe(t, tab, 4 * (j - 1));
         F::mul(t, t, zi2);
@@ -336,6 +340,18 @@ SG_HD void sw_build_table(const TabRef& tab, const Fe& x, const Fe& y) {
         F::mul(t, t, zi2);
         tab_store_fe(tab, 4 * (j - 1) + 2, t);
     }
+}
+
+// one table on its own (unit shims)
+template <class C>
+SG_HD void sw_build_table(const TabRef& tab, const Fe& x, const Fe& y) {
+    typedef typename C::F F;
+    Fe one, c, inv;
+    F::set_one(one);
+    c = one;
+    sw_table_park<C>(tab, x, y, c);
+    fe_inv((F*)0, inv, c);
+    sw_table_normalize<C>(tab, inv, one);
 }
 
 // acc += sign(d) * |d| * R (optionally mapped through the endomorphism (x,y) -> (beta*x, y))
@@ -496,81 +512,194 @@ SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabR
     }
 }
 
-// One signature.  sig_w / msg_w: the 64 / 32 input bytes as little-endian-loaded 32-bit words.
-// out_w: 16 words (X || Y big-endian bytes, again as little-endian-loaded words); all zero when invalid.
-// Returns the status byte: 0 = recovered, 1 = invalid signature (the CPU libraries' Err(InvalidSignature)).
-template <class C, bool kSync>
-SG_HD u32 sw_ecrecover_one(u32* out_w, const u32* sig_w, const u32* msg_w, const TabRef& tab, const u32* gtab) {
-    typedef typename C::F F;
-    typedef typename C::S S;
-    // decode_signature: y parity is bit 7 of byte 32 (src/wgsl/signature.wgsl:6-21, src/tests/mod.rs:151-163)
+// ---------------------------------------------------------------------------------------------------------
+// Batched recovery: one thread walks B <= kSwBatch signatures through the per-signature program phase by phase, so that
+// each of the three modular inversions (r^-1 mod n, the table normalisation, Z^-1 of the result) is paid once per B
+// signatures by Montgomery's trick (3-4 products per signature instead of a ~25 k-instruction safegcd each: the
+// inversions were 16% of all issued instructions, profiles/r01_ncu_instruction_mix.txt).
+//
+// IO supplies the rows:  io.load(j, sig_w[16], msg_w[8])  and  io.store(j, out_w[16], status).
+// sig_w / msg_w are the 64 / 32 input bytes as little-endian-loaded 32-bit words; out_w is X || Y big-endian bytes (again
+// as LE-loaded words), all zero when the status is 1 = invalid signature (the CPU libraries' Err(InvalidSignature)).
+// Per-thread scratch, in 16-byte chunks: B tables of kSwTabChunks, then per signature the r-chain slot (2), the
+// Jacobian result (6) and the Z-chain slot (2).
+// ---------------------------------------------------------------------------------------------------------
+static constexpr int kSwBatch = 8;
+static constexpr int kSwBatchChunks = kSwBatch * (kSwTabChunks + 10);
+
+SG_HD TabRef tab_offset(const TabRef& t, int chunks) {
+    TabRef r;
+    r.base = t.base + (size_t)chunks * t.stride;
+    r.stride = t.stride;
+    return r;
+}
+
+struct SwParsed {
     u32 r[8], s[8], z[8];
-    be_words_to_limbs(r, sig_w);
+    u32 parity;
+    bool ok;
+};
+
+// decode_signature (y parity = bit 7 of byte 32: src/wgsl/signature.wgsl:6-21, src/tests/mod.rs:151-163) + range checks.
+// A rejected signature keeps walking the program on substitute values (r = s = 1) -- no early exit, every thread of the
+// block reaches every barrier -- and its outputs are zeroed at the end.
+template <class C>
+SG_HD void sw_parse(SwParsed& p, const u32* sig_w, const u32* msg_w) {
+    typedef typename C::S S;
+    be_words_to_limbs(p.r, sig_w);
     u32 sw[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) sw[i] = sig_w[8 + i];
-    u32 parity = (sw[0] >> 7) & 1u;
+    p.parity = (sw[0] >> 7) & 1u;
     sw[0] &= ~0x80u;
-    be_words_to_limbs(s, sw);
-    be_words_to_limbs(z, msg_w);
-    // No early exit: a rejected signature keeps walking the same program on substitute values (r = s = 1, R = G) so
-    // that every thread of the block reaches every phase barrier; its outputs are zeroed at the end.
-    bool ok = !(is_zero8(r) || is_zero8(s) || !S::lt_mod(r) || !S::lt_mod(s));
-    if (!ok) {
+    be_words_to_limbs(p.s, sw);
+    be_words_to_limbs(p.z, msg_w);
+    p.ok = !(is_zero8(p.r) || is_zero8(p.s) || !S::lt_mod(p.r) || !S::lt_mod(p.s));
+    if (!p.ok) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) r[i] = s[i] = (i == 0) ? 1u : 0u;
+        for (int i = 0; i < 8; i++) p.r[i] = p.s[i] = (i == 0) ? 1u : 0u;
     }
-    S::reduce_once(z, z);
-    // lift x = r
-    Fe x, y, t, y2;
-    F::from_plain(x, r);
-    C::rhs(t, x);
-    phase_sync<kSync>();
-    fe_sqrt_candidate((F*)0, y, t);
-    F::sqr(y2, y);
-    if (!F::eq(y2, t)) {  // x = r is not on the curve: invalid; continue with R = G
-        ok = false;
-        F::from_table(x, gtab);
-        F::from_table(y, gtab + 8);
-    }
+    S::reduce_once(p.z, p.z);
+}
+
+template <class C, bool kSync, class IO>
+SG_HD void sw_ecrecover_batch(int B, IO& io, const TabRef& scratch, const u32* gtab) {
+    typedef typename C::F F;
+    typedef typename C::S S;
+    const int kSA = kSwBatch * kSwTabChunks, kQ = kSA + 2 * kSwBatch, kZP = kQ + 6 * kSwBatch;
+    u32 sig_w[16], msg_w[8];
+    SwParsed p;
+    u32 bad = 0;  // bit j: signature j of the batch is invalid
+
+    // ---- phase A: r_j^-1 mod n for the whole batch (Montgomery domain: values carry a factor 2^256) ----
     {
-        u32 yp[8];
-        F::to_plain(yp, y);
-        if ((yp[0] & 1u) != parity) F::neg(y, y);
+        u32 c[8], rm[8], inv[8], t[8];
+        Fe tmp;
+#pragma unroll 1
+        for (int j = 0; j < B; j++) {
+            io.load(j, sig_w, msg_w);
+            sw_parse<C>(p, sig_w, msg_w);
+            S::to_mont(rm, p.r);
+            if (j == 0)
+                copy8(c, rm);
+            else
+                S::mmul(c, c, rm);
+            copy8(tmp.v, c);
+            tab_store_fe(scratch, kSA + 2 * j, tmp);
+        }
+        phase_sync<kSync>();
+        S::inv_plain(inv, c);  // (prod r * R)^-1 = (prod r)^-1 R^-1
+        S::r3(t);
+        S::mmul(inv, inv, t);  // (prod r)^-1 R
+#pragma unroll 1
+        for (int j = B - 1; j >= 0; j--) {
+            io.load(j, sig_w, msg_w);
+            sw_parse<C>(p, sig_w, msg_w);
+            S::to_mont(rm, p.r);
+            if (j > 0) {
+                tab_load_fe(tmp, scratch, kSA + 2 * (j - 1));
+                S::mmul(t, inv, tmp.v);  // r_j^-1 R
+                S::mmul(inv, inv, rm);
+            } else {
+                copy8(t, inv);
+            }
+            copy8(tmp.v, t);
+            tab_store_fe(scratch, kSA + 2 * j, tmp);
+        }
     }
-    // u1 = -z/r, u2 = s/r  (mod n)
-    u32 rinv[8], u1[8], u2[8];
-    phase_sync<kSync>();
-    S::inv_plain(rinv, r);     // r^-1 mod n by safegcd (modinv.cuh)
-    S::to_mont(rinv, rinv);    // r^-1 * 2^256 mod n, so that one Montgomery product gives the plain result
-    S::mmul(u2, rinv, s);
-    S::mmul(u1, rinv, z);
-    S::neg(u1, u1);
-    // Q = u1*G + u2*R
-    phase_sync<kSync>();
-    sw_build_table<C>(tab, x, y);
-    JacPoint Q;
-    sw_double_mul<C, kSync>(Q, u1, u2, tab, gtab);
-    phase_sync<kSync>();
-    if (Q.inf) {  // Q = infinity: invalid; keep the inversion well defined
-        ok = false;
-        F::set_one(Q.Z);
+    // ---- phase B1: lift x = r, Jacobian multiples 2R..8R of every signature, one inversion, affine tables ----
+    {
+        Fe one, c, inv;
+        F::set_one(one);
+        c = one;
+#pragma unroll 1
+        for (int j = 0; j < B; j++) {
+            phase_sync<kSync>();
+            io.load(j, sig_w, msg_w);
+            sw_parse<C>(p, sig_w, msg_w);
+            if (!p.ok) bad |= 1u << j;
+            Fe x, y, t, y2;
+            F::from_plain(x, p.r);
+            C::rhs(t, x);
+            fe_sqrt_candidate((F*)0, y, t);
+            F::sqr(y2, y);
+            if (!F::eq(y2, t)) {  // x = r is not on the curve: invalid; continue with R = G
+                bad |= 1u << j;
+                F::from_table(x, gtab);
+                F::from_table(y, gtab + 8);
+            }
+            {
+                u32 yp[8];
+                F::to_plain(yp, y);
+                if ((yp[0] & 1u) != p.parity) F::neg(y, y);
+            }
+            sw_table_park<C>(tab_offset(scratch, j * kSwTabChunks), x, y, c);
+        }
+        phase_sync<kSync>();
+        fe_inv((F*)0, inv, c);
+#pragma unroll 1
+        for (int j = B - 1; j >= 0; j--) {
+            Fe c_before = one;
+            if (j > 0) tab_load_fe(c_before, tab_offset(scratch, (j - 1) * kSwTabChunks), kSwTabC + 2 * 6);
+            sw_table_normalize<C>(tab_offset(scratch, j * kSwTabChunks), inv, c_before);
+        }
     }
-    Fe zi, zi2, ax, ay;
-    fe_inv((F*)0, zi, Q.Z);
-    F::sqr(zi2, zi);
-    F::mul(ax, Q.X, zi2);
-    F::mul(zi2, zi2, zi);
-    F::mul(ay, Q.Y, zi2);
-    u32 xp[8], yp[8];
-    F::to_plain(xp, ax);
-    F::to_plain(yp, ay);
+    // ---- phase B2: u1 = -z/r, u2 = s/r, Q = u1*G + u2*R; Jacobian results parked, running product of their Z ----
+    {
+        Fe one, c, inv;
+        F::set_one(one);
+        c = one;
+#pragma unroll 1
+        for (int j = 0; j < B; j++) {
+            phase_sync<kSync>();
+            io.load(j, sig_w, msg_w);
+            sw_parse<C>(p, sig_w, msg_w);
+            Fe rinv;
+            tab_load_fe(rinv, scratch, kSA + 2 * j);
+            u32 u1[8], u2[8];
+            S::mmul(u2, rinv.v, p.s);
+            S::mmul(u1, rinv.v, p.z);
+            S::neg(u1, u1);
+            JacPoint Q;
+            sw_double_mul<C, kSync>(Q, u1, u2, tab_offset(scratch, j * kSwTabChunks), gtab);
+            if (Q.inf) {  // Q = infinity: invalid; keep the chain invertible
+                bad |= 1u << j;
+                F::set_one(Q.Z);
+            }
+            tab_store_fe(scratch, kQ + 6 * j, Q.X);
+            tab_store_fe(scratch, kQ + 6 * j + 2, Q.Y);
+            tab_store_fe(scratch, kQ + 6 * j + 4, Q.Z);
+            F::mul(c, c, Q.Z);
+            tab_store_fe(scratch, kZP + 2 * j, c);
+        }
+        phase_sync<kSync>();
+        fe_inv((F*)0, inv, c);
+        // ---- phase C: affine coordinates, big-endian bytes, status ----
+#pragma unroll 1
+        for (int j = B - 1; j >= 0; j--) {
+            Fe X, Y, Z, zi, zi2, ax, ay, cp = one;
+            tab_load_fe(X, scratch, kQ + 6 * j);
+            tab_load_fe(Y, scratch, kQ + 6 * j + 2);
+            tab_load_fe(Z, scratch, kQ + 6 * j + 4);
+            if (j > 0) tab_load_fe(cp, scratch, kZP + 2 * (j - 1));
+            F::mul(zi, inv, cp);
+            F::mul(inv, inv, Z);
+            F::sqr(zi2, zi);
+            F::mul(ax, X, zi2);
+            F::mul(zi2, zi2, zi);
+            F::mul(ay, Y, zi2);
+            u32 xp[8], yp[8], out_w[16];
+            F::to_plain(xp, ax);
+            F::to_plain(yp, ay);
+            const bool ok = ((bad >> j) & 1u) == 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        out_w[i] = ok ? bswap32(xp[7 - i]) : 0u;
-        out_w[8 + i] = ok ? bswap32(yp[7 - i]) : 0u;
+            for (int i = 0; i < 8; i++) {
+                out_w[i] = ok ? bswap32(xp[7 - i]) : 0u;
+                out_w[8 + i] = ok ? bswap32(yp[7 - i]) : 0u;
+            }
+            io.store(j, out_w, ok ? 0u : 1u);
+        }
     }
-    return ok ? 0u : 1u;
 }
 
 }  // namespace sigops

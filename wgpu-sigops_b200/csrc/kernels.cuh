@@ -40,23 +40,17 @@ static constexpr bool kInnerSync = true;
 
 #if defined(__CUDACC__)
 
-template <class C>
-__global__ void __launch_bounds__(kBlock, SG_MINB_SW) ecrecover_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
-                                                           size_t n, Q4* __restrict__ out, uint8_t* __restrict__ status,
-                                                           Q4* __restrict__ scratch, const u32* __restrict__ gtab) {
-    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
-    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    TabRef tab;
-    tab.base = scratch + gid;
-    tab.stride = (u32)nthreads;
-    // Uniform trip count per block: lanes past the end redo the last signature and drop the result, so that every thread
-    // reaches every phase barrier.
-    for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += nthreads) {
-        phase_sync<true>();
-        size_t i = base + threadIdx.x;
-        const bool live = i < n;
-        if (!live) i = n - 1;
-        u32 sig_w[16], msg_w[8], out_w[16];
+// Row access of one thread's batch: item j of the batch is row first + j * stride of the shard.  Rows past the end are
+// clamped on load (the thread redoes the last signature so that it reaches every barrier) and dropped on store.
+struct SwDeviceIO {
+    const Q4* sigs;
+    const Q4* msgs;
+    Q4* out;
+    uint8_t* status;
+    size_t n, first, stride;
+    __device__ __forceinline__ void load(int j, u32* sig_w, u32* msg_w) const {
+        size_t i = first + (size_t)j * stride;
+        if (i >= n) i = n - 1;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             Q4 v = sigs[4 * i + q];
@@ -73,33 +67,49 @@ __global__ void __launch_bounds__(kBlock, SG_MINB_SW) ecrecover_kernel(const Q4*
             msg_w[4 * q + 2] = v.z;
             msg_w[4 * q + 3] = v.w;
         }
-        u32 st = sw_ecrecover_one<C, kInnerSync>(out_w, sig_w, msg_w, tab, gtab);
-        if (live) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                Q4 v = {out_w[4 * q + 0], out_w[4 * q + 1], out_w[4 * q + 2], out_w[4 * q + 3]};
-                out[4 * i + q] = v;
-            }
-            if (status) status[i] = (uint8_t)st;
-        }
     }
-}
+    __device__ __forceinline__ void store(int j, const u32* out_w, u32 st) const {
+        const size_t i = first + (size_t)j * stride;
+        if (i >= n) return;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            Q4 v = {out_w[4 * q + 0], out_w[4 * q + 1], out_w[4 * q + 2], out_w[4 * q + 3]};
+            out[4 * i + q] = v;
+        }
+        if (status) status[i] = (uint8_t)st;
+    }
+};
 
-__global__ void __launch_bounds__(kBlock, SG_MINB_ED) ed25519_verify_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
-                                                                const Q4* __restrict__ pks, size_t n,
-                                                                uint8_t* __restrict__ valid, Q4* __restrict__ scratch,
-                                                                const u32* __restrict__ btab) {
+template <class C>
+__global__ void __launch_bounds__(kBlock, SG_MINB_SW) ecrecover_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
+                                                                       size_t n, Q4* __restrict__ out, uint8_t* __restrict__ status,
+                                                                       Q4* __restrict__ scratch, const u32* __restrict__ gtab) {
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     TabRef tab;
     tab.base = scratch + gid;
     tab.stride = (u32)nthreads;
-    for (size_t base = (size_t)blockIdx.x * blockDim.x; base < n; base += nthreads) {
+    SwDeviceIO io = {sigs, msgs, out, status, n, 0, nthreads};
+    // Each thread takes the rows gid, gid + T, gid + 2T, ... (T = threads in the grid) in batches of up to kSwBatch; the
+    // batch size is uniform over the grid, so every thread of a block reaches every barrier.
+    const size_t passes = (n + nthreads - 1) / nthreads;
+    for (size_t pass = 0; pass < passes; pass += kSwBatch) {
+        const int B = (int)((passes - pass) < (size_t)kSwBatch ? (passes - pass) : (size_t)kSwBatch);
         phase_sync<true>();
-        size_t i = base + threadIdx.x;
-        const bool live = i < n;
-        if (!live) i = n - 1;
-        u32 sig_w[16], msg_w[8], pk_w[8];
+        io.first = pass * nthreads + gid;
+        sw_ecrecover_batch<C, kInnerSync>(B, io, tab, gtab);
+    }
+}
+
+struct EdDeviceIO {
+    const Q4* sigs;
+    const Q4* msgs;
+    const Q4* pks;
+    uint8_t* valid;
+    size_t n, first, stride;
+    __device__ __forceinline__ void load(int j, u32* sig_w, u32* msg_w, u32* pk_w) const {
+        size_t i = first + (size_t)j * stride;
+        if (i >= n) i = n - 1;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             Q4 v = sigs[4 * i + q];
@@ -121,8 +131,29 @@ __global__ void __launch_bounds__(kBlock, SG_MINB_ED) ed25519_verify_kernel(cons
             pk_w[4 * q + 2] = p.z;
             pk_w[4 * q + 3] = p.w;
         }
-        const u32 v = ed_verify_one<kInnerSync>(sig_w, msg_w, pk_w, tab, btab);
-        if (live) valid[i] = (uint8_t)v;
+    }
+    __device__ __forceinline__ void store(int j, u32 v) const {
+        const size_t i = first + (size_t)j * stride;
+        if (i < n) valid[i] = (uint8_t)v;
+    }
+};
+
+__global__ void __launch_bounds__(kBlock, SG_MINB_ED) ed25519_verify_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
+                                                                            const Q4* __restrict__ pks, size_t n,
+                                                                            uint8_t* __restrict__ valid, Q4* __restrict__ scratch,
+                                                                            const u32* __restrict__ btab) {
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TabRef tab;
+    tab.base = scratch + gid;
+    tab.stride = (u32)nthreads;
+    EdDeviceIO io = {sigs, msgs, pks, valid, n, 0, nthreads};
+    const size_t passes = (n + nthreads - 1) / nthreads;
+    for (size_t pass = 0; pass < passes; pass += kEdBatch) {
+        const int B = (int)((passes - pass) < (size_t)kEdBatch ? (passes - pass) : (size_t)kEdBatch);
+        phase_sync<true>();
+        io.first = pass * nthreads + gid;
+        ed_verify_batch<kInnerSync>(B, io, tab, btab);
     }
 }
 

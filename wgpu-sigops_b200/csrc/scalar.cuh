@@ -27,6 +27,10 @@ struct ModK1N {
         const u32 M[8] = SG_K1_N_R2;
         copy8(m, M);
     }
+    static SG_HD void r3(u32* m) {
+        const u32 M[8] = SG_K1_N_R3;
+        copy8(m, M);
+    }
     static SG_HD void minus2(u32* m) {
         const u32 M[8] = SG_K1_N_MINUS2;
         copy8(m, M);
@@ -43,6 +47,10 @@ struct ModR1N {
         const u32 M[8] = SG_R1_N_R2;
         copy8(m, M);
     }
+    static SG_HD void r3(u32* m) {
+        const u32 M[8] = SG_R1_N_R3;
+        copy8(m, M);
+    }
     static SG_HD void minus2(u32* m) {
         const u32 M[8] = SG_R1_N_MINUS2;
         copy8(m, M);
@@ -56,6 +64,10 @@ struct ModEdL {
     }
     static SG_HD void r2(u32* m) {
         const u32 M[8] = SG_ED_L_R2;
+        copy8(m, M);
+    }
+    static SG_HD void r3(u32* m) {
+        const u32 M[8] = SG_ED_L_R3;
         copy8(m, M);
     }
     static SG_HD void minus2(u32* m) {
@@ -161,6 +173,7 @@ struct Sc {
         M::mod(m);
         return !gte8(a, m);
     }
+    static SG_HD void r3(u32* r) { M::r3(r); }  // 2^768 mod m
     // plain inverse a^-1 mod m for a in [0, m): safegcd
     static SG_HD void inv_plain(u32* r, const u32* a) { ModInv<typename M::MI>::inv(r, a); }
     // Montgomery-domain inverse by Fermat: a^(m-2), fixed 4-bit windows (256 squarings + 64 + 14 products).

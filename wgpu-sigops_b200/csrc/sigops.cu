@@ -197,7 +197,7 @@ int launch_op(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_msgs, co
     }
     size_t blocks = (n + tpb - 1) / tpb;
     int grid = (int)std::min<size_t>(blocks, (size_t)max_g);
-    size_t chunks = op == OP_ED ? kEdTabChunks : kSwTabChunks;
+    size_t chunks = op == OP_ED ? kEdBatchChunks : kSwBatchChunks;
     if (ensure_scratch(d, chunks * (size_t)max_g * kBlock)) return 1;
     switch (op) {
         case OP_K1:
