@@ -223,7 +223,7 @@ int launch_op(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_msgs, co
 // piece's upload and the last piece's download are exposed.  Kernels run back to back on ONE stream: they share the
 // per-thread scratch tables.
 constexpr int kMaxChunks = 8;
-constexpr size_t kMinWaves = 3;  // >= 3 passes (~7 ms of kernel) per piece
+constexpr size_t kLeadWaves = 2;  // passes in the first, short piece (~4 ms of kernel): exposed upload ~0.3 ms
 
 int run_shard(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n, uint8_t* out,
               uint8_t* status) {
@@ -239,13 +239,21 @@ int run_shard(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs, const 
     uint8_t* d_status = op == OP_ED ? nullptr : d.d_out + n * 64;
     int max_chunks = kMaxChunks;
     if (const char* e = getenv("SIGOPS_MAX_CHUNKS")) max_chunks = std::max(1, std::min(kMaxChunks, atoi(e)));
-    // pieces are whole multiples of one wave (SMs x 512 threads, one signature per thread per pass) so that only the
-    // last piece ends on a partial wave; at least kMinWaves waves per piece
+    // Pieces are whole multiples of one wave (SMs x 512 threads, one signature per thread per pass) so that only the last
+    // piece ends on a partial wave.  The first piece is short (kLeadWaves) so that the kernels start early; the rest is
+    // cut into equal pieces of at most kSwBatch waves -- one full shared-inversion batch per thread (curve_sw.cuh).
     const size_t wave = (size_t)d.sms * kBlock;
     const size_t n_waves = (n + wave - 1) / wave;
-    int chunks = (int)std::min<size_t>((size_t)max_chunks, std::max<size_t>(1, n_waves / kMinWaves));
     size_t bounds[kMaxChunks + 1];
-    for (int c = 0; c <= chunks; c++) bounds[c] = std::min(n, (n_waves * (size_t)c / chunks) * wave);
+    int chunks = 1;
+    bounds[0] = 0;
+    if (max_chunks > 1 && n_waves >= 2 * kLeadWaves + 1) {
+        const size_t rest = n_waves - kLeadWaves;
+        const int rest_chunks = (int)std::min<size_t>((size_t)max_chunks - 1, (rest + kSwBatch - 1) / kSwBatch);
+        chunks = 1 + rest_chunks;
+        bounds[1] = kLeadWaves * wave;
+        for (int c = 1; c <= rest_chunks; c++) bounds[1 + c] = std::min(n, (kLeadWaves + rest * (size_t)c / rest_chunks) * wave);
+    }
     bounds[chunks] = n;
     CK(cudaEventRecord(d.ev[0], d.s_in));
     for (int c = 0; c < chunks; c++) {
