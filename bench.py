@@ -443,6 +443,14 @@ def run_sigops(args):
                          f"4x64 Montgomery, wNAF Strauss-Shamir), {threads} pthreads; the Rust reference CPU path "
                          "(fuel-crypto -> libsecp256k1) cannot be built here (no rustc)"}
 
+    # Independent production-grade reference points on the same host cores: OpenSSL 3 (via `cryptography`) single-thread
+    # ECDSA *verify* on P-256 / secp256k1 and Ed25519 verify -- "verify, not recover; OpenSSL, not fuel-crypto" (BASELINE.md 3).
+    if cpu is not None:
+        try:
+            cpu["openssl_single_thread"] = _openssl_points()
+        except Exception as e:  # the numbers are context only
+            cpu["openssl_single_thread"] = {"unavailable": str(e)[:120]}
+
     if rank == 0:
         head = results.get("secp256k1") or next(iter(results.values()))
         hbm_peak, hbm_src = _hbm_peak()
@@ -473,6 +481,34 @@ def run_sigops(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def _openssl_points(reps: int = 1500):
+    import hashlib
+
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric import ec, ed25519, utils
+
+    out = {}
+    z = hashlib.sha256(b"bench").digest()
+    for name, curve in (("p256_ecdsa_verify", ec.SECP256R1()), ("secp256k1_ecdsa_verify", ec.SECP256K1())):
+        key = ec.generate_private_key(curve)
+        sig = key.sign(z, ec.ECDSA(utils.Prehashed(hashes.SHA256())))
+        pub = key.public_key()
+        alg = ec.ECDSA(utils.Prehashed(hashes.SHA256()))
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            pub.verify(sig, z, alg)
+        out[name] = {"value": reps / (time.perf_counter() - t0), "unit": "verifies/s"}
+    key = ed25519.Ed25519PrivateKey.generate()
+    sig = key.sign(z)
+    pub = key.public_key()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        pub.verify(sig, z)
+    out["ed25519_verify"] = {"value": reps / (time.perf_counter() - t0), "unit": "verifies/s"}
+    out["note"] = "OpenSSL 3 through the Python `cryptography` binding (includes ~5 us of binding overhead per call), one thread"
+    return out
 
 
 def _hbm_peak():
