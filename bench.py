@@ -371,7 +371,7 @@ def run_sigops(args):
         ext = {"ed25519_verify_strict_msgs": {"e2e": {"value": n * args.steps / dt, "unit": "sigs/s"},
                                               "kernel_value": n / (ker.value * 1e-3), "unit": "sigs/s",
                                               "note": "sigops_ed25519_ecverify_msgs, flags = STRICT, 1M signatures, 32-byte messages "
-                                                      "through the offsets array; one upload / kernel / download (no piecewise overlap)"}}
+                                                      "through the offsets array"}}
         for ptr in (p_s, p_m, p_k, p_o, p_v):
             lib.sigops_host_free(ptr)
         log(f"[rank 0] ed25519 strict/msgs: {n / (ker.value * 1e-3) / 1e6:.2f} M sigs/s kernel, {n * args.steps / dt / 1e6:.2f} M sigs/s e2e")
@@ -418,7 +418,7 @@ def run_sigops(args):
         ext["secp256k1_raw_messages_to_addresses"] = {
             "e2e": {"value": n * args.steps / dt, "unit": "sigs/s"}, "kernel_value": n / (ker.value * 1e-3), "unit": "sigs/s",
             "note": "sigops_ecrecover_addresses: SHA-256(message) + recover + SHA-256(X||Y) in three kernels on one stream, "
-                    "1M signatures, 32-byte raw messages; one upload / download per call (no piecewise overlap)"}
+                    "1M signatures, 32-byte raw messages"}
         for ptr in (p_s, p_m, p_o, p_a, p_k, p_t):
             lib.sigops_host_free(ptr)
         log(f"[rank 0] k1 raw->address: {n / (ker.value * 1e-3) / 1e6:.2f} M sigs/s kernels, {n * args.steps / dt / 1e6:.2f} M sigs/s e2e")

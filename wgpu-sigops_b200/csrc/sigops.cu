@@ -225,26 +225,14 @@ int launch_op(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_msgs, co
 constexpr int kMaxChunks = 8;
 constexpr size_t kLeadWaves = 2;  // passes in the first, short piece (~4 ms of kernel): exposed upload ~0.3 ms
 
-int run_shard(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n, uint8_t* out,
-              uint8_t* status) {
-    CK(cudaSetDevice(d.id));
-    const size_t in_bytes = n * (op == OP_ED ? 128 : 96);
-    const size_t out_stride = op == OP_ED ? 1 : 64;
-    const size_t out_bytes = op == OP_ED ? n : n * 65;
-    if (ensure_buf(&d.d_in, &d.in_cap, in_bytes + 64)) return 1;
-    if (ensure_buf(&d.d_out, &d.out_cap, out_bytes + 64)) return 1;
-    uint8_t* d_sigs = d.d_in;
-    uint8_t* d_msgs = d.d_in + n * 64;
-    uint8_t* d_pks = d.d_in + n * 96;
-    uint8_t* d_status = op == OP_ED ? nullptr : d.d_out + n * 64;
+// Piece plan: pieces are whole multiples of one wave (SMs x 512 threads, one signature per thread per pass) so that only
+// the last piece ends on a partial wave.  The first piece is short (kLeadWaves) so that the kernels start early; the rest
+// is cut into equal pieces of at most kSwBatch waves -- one full shared-inversion batch per thread (curve_sw.cuh).
+int plan_pieces(const Device& d, size_t n, size_t* bounds) {
     int max_chunks = kMaxChunks;
     if (const char* e = getenv("SIGOPS_MAX_CHUNKS")) max_chunks = std::max(1, std::min(kMaxChunks, atoi(e)));
-    // Pieces are whole multiples of one wave (SMs x 512 threads, one signature per thread per pass) so that only the last
-    // piece ends on a partial wave.  The first piece is short (kLeadWaves) so that the kernels start early; the rest is
-    // cut into equal pieces of at most kSwBatch waves -- one full shared-inversion batch per thread (curve_sw.cuh).
     const size_t wave = (size_t)d.sms * kBlock;
     const size_t n_waves = (n + wave - 1) / wave;
-    size_t bounds[kMaxChunks + 1];
     int chunks = 1;
     bounds[0] = 0;
     if (max_chunks > 1 && n_waves >= 2 * kLeadWaves + 1) {
@@ -255,28 +243,32 @@ int run_shard(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs, const 
         for (int c = 1; c <= rest_chunks; c++) bounds[1 + c] = std::min(n, (kLeadWaves + rest * (size_t)c / rest_chunks) * wave);
     }
     bounds[chunks] = n;
+    return chunks;
+}
+
+// The three-stage pipeline over the pieces of one shard.  up(lo, m, stream) enqueues the uploads of piece [lo, lo + m),
+// launch(lo, m, stream) its kernels, down(lo, m, stream) its downloads; each returns nonzero on failure.
+template <class Up, class Launch, class Down>
+int run_pipeline(Device& d, size_t n, Up up, Launch launch, Down down) {
+    size_t bounds[kMaxChunks + 1];
+    const int chunks = plan_pieces(d, n, bounds);
     CK(cudaEventRecord(d.ev[0], d.s_in));
     for (int c = 0; c < chunks; c++) {
-        const size_t lo = bounds[c], hi = bounds[c + 1], m = hi - lo;
-        CK(cudaMemcpyAsync(d_sigs + lo * 64, sigs + lo * 64, m * 64, cudaMemcpyHostToDevice, d.s_in));
-        CK(cudaMemcpyAsync(d_msgs + lo * 32, msgs + lo * 32, m * 32, cudaMemcpyHostToDevice, d.s_in));
-        if (op == OP_ED) CK(cudaMemcpyAsync(d_pks + lo * 32, pks + lo * 32, m * 32, cudaMemcpyHostToDevice, d.s_in));
+        const size_t lo = bounds[c], m = bounds[c + 1] - lo;
+        if (up(lo, m, d.s_in)) return 1;
         CK(cudaEventRecord(d.ev_in[c], d.s_in));
         CK(cudaStreamWaitEvent(d.stream, d.ev_in[c], 0));
         if (c == 0) CK(cudaEventRecord(d.ev[1], d.stream));
-        if (launch_op(d, op, d_sigs + lo * 64, d_msgs + lo * 32, d_pks + lo * 32, m, d.d_out + lo * out_stride,
-                      d_status ? d_status + lo : nullptr, d.stream))
-            return 1;
+        if (launch(lo, m, d.stream)) return 1;
         CK(cudaEventRecord(d.ev_k[c], d.stream));
     }
     CK(cudaEventRecord(d.ev[2], d.stream));
     // downloads are enqueued after every upload and kernel: a download into pageable memory blocks the calling thread
     // until its kernel has finished, which would otherwise stall the staging of the next piece's upload
     for (int c = 0; c < chunks; c++) {
-        const size_t lo = bounds[c], hi = bounds[c + 1], m = hi - lo;
+        const size_t lo = bounds[c], m = bounds[c + 1] - lo;
         CK(cudaStreamWaitEvent(d.s_out, d.ev_k[c], 0));
-        CK(cudaMemcpyAsync(out + lo * out_stride, d.d_out + lo * out_stride, m * out_stride, cudaMemcpyDeviceToHost, d.s_out));
-        if (op != OP_ED && status) CK(cudaMemcpyAsync(status + lo, d_status + lo, m, cudaMemcpyDeviceToHost, d.s_out));
+        if (down(lo, m, d.s_out)) return 1;
     }
     CK(cudaEventRecord(d.ev[3], d.s_out));
     CK(cudaStreamSynchronize(d.s_out));
@@ -289,6 +281,36 @@ int run_shard(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs, const 
     CK(cudaEventElapsedTime(&d.ms_d2h, d.ev[2], d.ev[3]));
     if (d.ms_d2h < 0) d.ms_d2h = 0;
     return 0;
+}
+
+int run_shard(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n, uint8_t* out,
+              uint8_t* status) {
+    CK(cudaSetDevice(d.id));
+    const size_t in_bytes = n * (op == OP_ED ? 128 : 96);
+    const size_t out_stride = op == OP_ED ? 1 : 64;
+    const size_t out_bytes = op == OP_ED ? n : n * 65;
+    if (ensure_buf(&d.d_in, &d.in_cap, in_bytes + 64)) return 1;
+    if (ensure_buf(&d.d_out, &d.out_cap, out_bytes + 64)) return 1;
+    uint8_t* d_sigs = d.d_in;
+    uint8_t* d_msgs = d.d_in + n * 64;
+    uint8_t* d_pks = d.d_in + n * 96;
+    uint8_t* d_status = op == OP_ED ? nullptr : d.d_out + n * 64;
+    auto up = [&](size_t lo, size_t m, cudaStream_t st) -> int {
+        CK(cudaMemcpyAsync(d_sigs + lo * 64, sigs + lo * 64, m * 64, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_msgs + lo * 32, msgs + lo * 32, m * 32, cudaMemcpyHostToDevice, st));
+        if (op == OP_ED) CK(cudaMemcpyAsync(d_pks + lo * 32, pks + lo * 32, m * 32, cudaMemcpyHostToDevice, st));
+        return 0;
+    };
+    auto launch = [&](size_t lo, size_t m, cudaStream_t st) -> int {
+        return launch_op(d, op, d_sigs + lo * 64, d_msgs + lo * 32, d_pks + lo * 32, m, d.d_out + lo * out_stride,
+                         d_status ? d_status + lo : nullptr, st);
+    };
+    auto down = [&](size_t lo, size_t m, cudaStream_t st) -> int {
+        CK(cudaMemcpyAsync(out + lo * out_stride, d.d_out + lo * out_stride, m * out_stride, cudaMemcpyDeviceToHost, st));
+        if (op != OP_ED && status) CK(cudaMemcpyAsync(status + lo, d_status + lo, m, cudaMemcpyDeviceToHost, st));
+        return 0;
+    };
+    return run_pipeline(d, n, up, launch, down);
 }
 
 // A device's shard is processed in sub-shards of at most kMaxSubShard signatures so that the device buffers stay
@@ -488,8 +510,8 @@ int sigops_ed25519_ecverify(const uint8_t* sigs, const uint8_t* msgs, const uint
     return run_batch(OP_ED, sigs, msgs, pks, n, out_valid, nullptr);
 }
 
-// Variable-length-message ed25519: one device shard = signatures [lo, hi) and the message bytes they span.  No piecewise
-// pipeline here (one upload, one kernel, one download per shard).
+// Variable-length-message ed25519: one device shard = signatures [lo, hi) and the message bytes they span, through the same
+// piecewise upload / kernel / download pipeline as the fixed-size entry points.
 static int run_ed_msgs_shard(Device& d, const uint8_t* sigs, const uint8_t* msg_bytes, const uint64_t* off, const uint8_t* pks,
                              size_t n, uint32_t flags, uint8_t* out) {
     CK(cudaSetDevice(d.id));
@@ -499,6 +521,7 @@ static int run_ed_msgs_shard(Device& d, const uint8_t* sigs, const uint8_t* msg_
     const size_t in_bytes = n * 96 + off_bytes + (size_t)nbytes + 64;
     if (ensure_buf(&d.d_in, &d.in_cap, in_bytes)) return 1;
     if (ensure_buf(&d.d_out, &d.out_cap, n + 64)) return 1;
+    if (ensure_scratch(d, (size_t)kEdTabChunks * d.grid_edm * kBlock)) return 1;
     uint8_t* d_sigs = d.d_in;
     uint8_t* d_pks = d.d_in + n * 64;
     uint8_t* d_off = d.d_in + n * 96;
@@ -511,32 +534,34 @@ static int run_ed_msgs_shard(Device& d, const uint8_t* sigs, const uint8_t* msg_
         }
         rebased[i] = off[i] - b0;
     }
-    CK(cudaEventRecord(d.ev[0], d.stream));
-    CK(cudaMemcpyAsync(d_sigs, sigs, n * 64, cudaMemcpyHostToDevice, d.stream));
-    CK(cudaMemcpyAsync(d_pks, pks, n * 32, cudaMemcpyHostToDevice, d.stream));
-    CK(cudaMemcpyAsync(d_off, rebased.data(), off_bytes, cudaMemcpyHostToDevice, d.stream));
-    if (nbytes) CK(cudaMemcpyAsync(d_msg, msg_bytes + b0, (size_t)nbytes, cudaMemcpyHostToDevice, d.stream));
-    CK(cudaEventRecord(d.ev[1], d.stream));
-    int tpb = kBlock;
-    if (n < (size_t)d.sms * kBlock) {
-        size_t per_sm = (n + d.sms - 1) / d.sms;
-        tpb = (int)std::min<size_t>(kBlock, std::max<size_t>(32, (per_sm + 31) / 32 * 32));
-    }
-    int grid = (int)std::min<size_t>((n + tpb - 1) / tpb, (size_t)d.grid_edm);
-    if (ensure_scratch(d, (size_t)kEdTabChunks * d.grid_edm * kBlock)) return 1;
-    ed25519_verify_msgs_kernel<<<grid, tpb, 0, d.stream>>>((const Q4*)d_sigs, d_msg, (const unsigned long long*)d_off,
-                                                           (const Q4*)d_pks, n, (int)(flags & SIGOPS_ED25519_STRICT),
-                                                           d.d_out, d.scratch, d.edb);
-    CK(cudaGetLastError());
-    g_launches++;
-    CK(cudaEventRecord(d.ev[2], d.stream));
-    CK(cudaMemcpyAsync(out, d.d_out, n, cudaMemcpyDeviceToHost, d.stream));
-    CK(cudaEventRecord(d.ev[3], d.stream));
-    CK(cudaStreamSynchronize(d.stream));
-    CK(cudaEventElapsedTime(&d.ms_h2d, d.ev[0], d.ev[1]));
-    CK(cudaEventElapsedTime(&d.ms_kernel, d.ev[1], d.ev[2]));
-    CK(cudaEventElapsedTime(&d.ms_d2h, d.ev[2], d.ev[3]));
-    return 0;
+    // the offsets go up first, in one piece (8 bytes per signature); `rebased` stays alive until the pipeline has drained
+    CK(cudaMemcpyAsync(d_off, rebased.data(), off_bytes, cudaMemcpyHostToDevice, d.s_in));
+    auto up = [&](size_t lo, size_t m, cudaStream_t st) -> int {
+        CK(cudaMemcpyAsync(d_sigs + lo * 64, sigs + lo * 64, m * 64, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_pks + lo * 32, pks + lo * 32, m * 32, cudaMemcpyHostToDevice, st));
+        const uint64_t bl = rebased[lo], bh = rebased[lo + m];
+        if (bh > bl) CK(cudaMemcpyAsync(d_msg + bl, msg_bytes + b0 + bl, (size_t)(bh - bl), cudaMemcpyHostToDevice, st));
+        return 0;
+    };
+    auto launch = [&](size_t lo, size_t m, cudaStream_t st) -> int {
+        int tpb = kBlock;
+        if (m < (size_t)d.sms * kBlock) {
+            size_t per_sm = (m + d.sms - 1) / d.sms;
+            tpb = (int)std::min<size_t>(kBlock, std::max<size_t>(32, (per_sm + 31) / 32 * 32));
+        }
+        int grid = (int)std::min<size_t>((m + tpb - 1) / tpb, (size_t)d.grid_edm);
+        ed25519_verify_msgs_kernel<<<grid, tpb, 0, st>>>((const Q4*)(d_sigs + lo * 64), d_msg,
+                                                         (const unsigned long long*)d_off + lo, (const Q4*)(d_pks + lo * 32), m,
+                                                         (int)(flags & SIGOPS_ED25519_STRICT), d.d_out + lo, d.scratch, d.edb);
+        CK(cudaGetLastError());
+        g_launches++;
+        return 0;
+    };
+    auto down = [&](size_t lo, size_t m, cudaStream_t st) -> int {
+        CK(cudaMemcpyAsync(out + lo, d.d_out + lo, m, cudaMemcpyDeviceToHost, st));
+        return 0;
+    };
+    return run_pipeline(d, n, up, launch, down);
 }
 
 int sigops_ed25519_ecverify_msgs(const uint8_t* sigs, const uint8_t* msg_bytes, const uint64_t* msg_offsets,
@@ -574,14 +599,14 @@ int sigops_ed25519_ecverify_msgs(const uint8_t* sigs, const uint8_t* msg_bytes, 
     return 0;
 }
 
-// raw messages -> SHA-256 -> recover -> SHA-256(pubkey), all on the device; one shard, one stream, no host pass
+// raw messages -> SHA-256 -> recover -> SHA-256(pubkey), all on the device, piece by piece; no host pass in between
 static int run_addresses_shard(Device& d, Op op, const uint8_t* sigs, const uint8_t* msg_bytes, const uint64_t* off, size_t n,
                                uint8_t* out_addr, uint8_t* out_pk, uint8_t* out_st) {
     CK(cudaSetDevice(d.id));
-    const uint64_t b0 = off ? off[0] : 0, nbytes = off ? off[n] - off[0] : (uint64_t)n * 32;
+    const uint64_t b0 = off ? off[0] : 0, nbytes = off ? off[n] - off[0] : 0;
     const size_t off_bytes = off ? (n + 1) * sizeof(uint64_t) : 0;
     // d_in: sigs | prehashes (n*32) | offsets | raw bytes        d_out: pubkeys (n*64) | status (n) | pad | addresses
-    const size_t in_bytes = n * 96 + off_bytes + (off ? (size_t)nbytes : 0) + 64;
+    const size_t in_bytes = n * 96 + off_bytes + (size_t)nbytes + 64;
     const size_t addr_off = (n * 65 + 63) / 64 * 64;
     if (ensure_buf(&d.d_in, &d.in_cap, in_bytes)) return 1;
     if (ensure_buf(&d.d_out, &d.out_cap, addr_off + n * 32 + 64)) return 1;
@@ -591,10 +616,8 @@ static int run_addresses_shard(Device& d, Op op, const uint8_t* sigs, const uint
     uint8_t* d_raw = d_off + off_bytes;
     uint8_t* d_status = d.d_out + n * 64;
     uint8_t* d_addr = d.d_out + addr_off;
-    CK(cudaEventRecord(d.ev[0], d.stream));
-    CK(cudaMemcpyAsync(d_sigs, sigs, n * 64, cudaMemcpyHostToDevice, d.stream));
+    std::vector<uint64_t> rebased(off ? n + 1 : 0);
     if (off) {
-        std::vector<uint64_t> rebased(n + 1);
         for (size_t i = 0; i <= n; i++) {
             if (off[i] < b0 || (i && off[i] < off[i - 1])) {
                 set_err("sigops_ecrecover_addresses: msg_offsets must be non-decreasing");
@@ -602,32 +625,39 @@ static int run_addresses_shard(Device& d, Op op, const uint8_t* sigs, const uint
             }
             rebased[i] = off[i] - b0;
         }
-        CK(cudaMemcpyAsync(d_off, rebased.data(), off_bytes, cudaMemcpyHostToDevice, d.stream));
-        if (nbytes) CK(cudaMemcpyAsync(d_raw, msg_bytes + b0, (size_t)nbytes, cudaMemcpyHostToDevice, d.stream));
-        CK(cudaStreamSynchronize(d.stream));  // `rebased` is pageable and goes out of scope
-        CK(cudaEventRecord(d.ev[1], d.stream));
-        sha256_msgs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>(d_raw, (const unsigned long long*)d_off, n,
-                                                                             (u32*)d_msgs);
+        CK(cudaMemcpyAsync(d_off, rebased.data(), off_bytes, cudaMemcpyHostToDevice, d.s_in));
+    }
+    auto up = [&](size_t lo, size_t m, cudaStream_t st) -> int {
+        CK(cudaMemcpyAsync(d_sigs + lo * 64, sigs + lo * 64, m * 64, cudaMemcpyHostToDevice, st));
+        if (off) {
+            const uint64_t bl = rebased[lo], bh = rebased[lo + m];
+            if (bh > bl) CK(cudaMemcpyAsync(d_raw + bl, msg_bytes + b0 + bl, (size_t)(bh - bl), cudaMemcpyHostToDevice, st));
+        } else {
+            CK(cudaMemcpyAsync(d_msgs + lo * 32, msg_bytes + lo * 32, m * 32, cudaMemcpyHostToDevice, st));
+        }
+        return 0;
+    };
+    auto launch = [&](size_t lo, size_t m, cudaStream_t st) -> int {
+        if (off) {
+            sha256_msgs_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_raw, (const unsigned long long*)d_off + lo, m,
+                                                                           (u32*)(d_msgs + lo * 32));
+            CK(cudaGetLastError());
+            g_launches++;
+        }
+        if (launch_op(d, op, d_sigs + lo * 64, d_msgs + lo * 32, nullptr, m, d.d_out + lo * 64, d_status + lo, st)) return 1;
+        sha256_pubkeys_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>((const u32*)(d.d_out + lo * 64), d_status + lo, m,
+                                                                          (u32*)(d_addr + lo * 32));
         CK(cudaGetLastError());
         g_launches++;
-    } else {
-        CK(cudaMemcpyAsync(d_msgs, msg_bytes, n * 32, cudaMemcpyHostToDevice, d.stream));
-        CK(cudaEventRecord(d.ev[1], d.stream));
-    }
-    if (launch_op(d, op, d_sigs, d_msgs, nullptr, n, d.d_out, d_status, d.stream)) return 1;
-    sha256_pubkeys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, d.stream>>>((const u32*)d.d_out, d_status, n, (u32*)d_addr);
-    CK(cudaGetLastError());
-    g_launches++;
-    CK(cudaEventRecord(d.ev[2], d.stream));
-    CK(cudaMemcpyAsync(out_addr, d_addr, n * 32, cudaMemcpyDeviceToHost, d.stream));
-    if (out_pk) CK(cudaMemcpyAsync(out_pk, d.d_out, n * 64, cudaMemcpyDeviceToHost, d.stream));
-    if (out_st) CK(cudaMemcpyAsync(out_st, d_status, n, cudaMemcpyDeviceToHost, d.stream));
-    CK(cudaEventRecord(d.ev[3], d.stream));
-    CK(cudaStreamSynchronize(d.stream));
-    CK(cudaEventElapsedTime(&d.ms_h2d, d.ev[0], d.ev[1]));
-    CK(cudaEventElapsedTime(&d.ms_kernel, d.ev[1], d.ev[2]));
-    CK(cudaEventElapsedTime(&d.ms_d2h, d.ev[2], d.ev[3]));
-    return 0;
+        return 0;
+    };
+    auto down = [&](size_t lo, size_t m, cudaStream_t st) -> int {
+        CK(cudaMemcpyAsync(out_addr + lo * 32, d_addr + lo * 32, m * 32, cudaMemcpyDeviceToHost, st));
+        if (out_pk) CK(cudaMemcpyAsync(out_pk + lo * 64, d.d_out + lo * 64, m * 64, cudaMemcpyDeviceToHost, st));
+        if (out_st) CK(cudaMemcpyAsync(out_st + lo, d_status + lo, m, cudaMemcpyDeviceToHost, st));
+        return 0;
+    };
+    return run_pipeline(d, n, up, launch, down);
 }
 
 int sigops_ecrecover_addresses(int curve, const uint8_t* sigs, const uint8_t* msg_bytes, const uint64_t* msg_offsets,
