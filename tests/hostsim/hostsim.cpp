@@ -81,9 +81,9 @@ int hostsim_ecrecover(int curve, const uint8_t* sigs, const uint8_t* msgs, size_
         const int B = (int)std::min<size_t>((size_t)batch, n - i);
         i += (size_t)B;
         if (curve == 0)
-            sw_ecrecover_batch<CurveK1, false>(B, io, tab, k1_gtab.data());
+            sw_ecrecover_batch<CurveK1, false>(B, io, tab, k1_gtab.data(), k1_gtab.data());
         else
-            sw_ecrecover_batch<CurveR1, false>(B, io, tab, r1_gtab.data());
+            sw_ecrecover_batch<CurveR1, false>(B, io, tab, r1_gtab.data(), r1_gtab.data());
         batch = batch == 1 ? kSwBatch : batch - 1;  // 8, 7, ..., 1, 8, ...: every batch size gets exercised
     }
     return 0;

@@ -431,7 +431,10 @@ SG_HD void phase_sync() {
 }
 
 template <class C, bool kSync>
-SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabRef& tab, const u32* gtab) {
+SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabRef& tab, const u32* gtab,
+                         const u32* gtab_global) {
+    // gtab: the j*G table (possibly the shared-memory copy); gtab_global: the full table in global memory, whose second
+    // half holds lambda*j*G for secp256k1
     typedef typename C::Hot H;
     acc.inf = true;
     C::F::set_zero(acc.X);
@@ -471,7 +474,7 @@ SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabR
                 if (gcount == 0) {
 #pragma unroll 1
                     for (int s = 2; s < 4; s++)
-                        sw_add_from_gtab<H>(acc, gtab + (s == 3 ? kGTabEntries * 16 : 0),
+                        sw_add_from_gtab<H>(acc, s == 3 ? gtab_global + kGTabEntries * 16 : gtab,
                                             recode_digit<kGWin>(kp[s], (i * 11) >> 5 /* i / 3 for i <= 30 */), flip[s]);
                     gcount = 2;
                 } else {
@@ -563,7 +566,7 @@ SG_HD void sw_parse(SwParsed& p, const u32* sig_w, const u32* msg_w) {
 }
 
 template <class C, bool kSync, class IO>
-SG_HD void sw_ecrecover_batch(int B, IO& io, const TabRef& scratch, const u32* gtab) {
+SG_HD void sw_ecrecover_batch(int B, IO& io, const TabRef& scratch, const u32* gtab, const u32* gtab_global) {
     typedef typename C::F F;
     typedef typename C::S S;
     const int kSA = kSwBatch * kSwTabChunks, kQ = kSA + 2 * kSwBatch, kZP = kQ + 6 * kSwBatch;
@@ -661,7 +664,7 @@ SG_HD void sw_ecrecover_batch(int B, IO& io, const TabRef& scratch, const u32* g
             S::mmul(u1, rinv.v, p.z);
             S::neg(u1, u1);
             JacPoint Q;
-            sw_double_mul<C, kSync>(Q, u1, u2, tab_offset(scratch, j * kSwTabChunks), gtab);
+            sw_double_mul<C, kSync>(Q, u1, u2, tab_offset(scratch, j * kSwTabChunks), gtab, gtab_global);
             if (Q.inf) {  // Q = infinity: invalid; keep the chain invertible
                 bad |= 1u << j;
                 F::set_one(Q.Z);

@@ -3,8 +3,8 @@
 // intermediate storage buffers between them), the unit-test shims (the role of src/wgsl/tests/*.wgsl) and
 // the integer-pipe micro-benchmark.
 //
-// Launch geometry: 1-D grid, 128 threads per block, a bounded number of blocks (a multiple of the SM count)
-// and a grid-stride loop over signatures -- no power-of-two padding, no 3-D workgroup lookup table
+// Launch geometry: 1-D grid of one 512-thread block per SM (smaller blocks spread over all SMs for small batches); thread t
+// owns rows t, t + T, t + 2T, ... of the shard -- no power-of-two padding, no 3-D workgroup lookup table
 // (src/benchmarks/mod.rs:10-53 `compute_num_workgroups`, src/secp256k1_ecdsa.rs:24-47).
 #pragma once
 #include "../../include/sigops.h"
@@ -39,6 +39,19 @@ static constexpr bool kInnerSync = true;
 #endif
 
 #if defined(__CUDACC__)
+
+// Fixed-base table staged in shared memory: with one block per SM the whole 227 KB is free, and a 2048-entry table
+// (128 KB for the secp curves' j*G, 192 KB for ed25519's Niels triples) fits.  `smem_words` == 0 (small batches, where
+// the copy would cost more than the gathers) leaves the table in global memory / L2.
+extern __shared__ __align__(16) u32 sg_smem_table[];
+__device__ __forceinline__ const u32* stage_table(const u32* __restrict__ gtab, u32 smem_words) {
+    if (smem_words == 0) return gtab;
+    const Q4* src = reinterpret_cast<const Q4*>(gtab);
+    Q4* dst = reinterpret_cast<Q4*>(sg_smem_table);
+    for (u32 i = threadIdx.x; i < smem_words / 4; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+    return sg_smem_table;
+}
 
 // Row access of one thread's batch: item j of the batch is row first + j * stride of the shard.  Rows past the end are
 // clamped on load (the thread redoes the last signature so that it reaches every barrier) and dropped on store.
@@ -83,7 +96,10 @@ struct SwDeviceIO {
 template <class C>
 __global__ void __launch_bounds__(kBlock, SG_MINB_SW) ecrecover_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
                                                                        size_t n, Q4* __restrict__ out, uint8_t* __restrict__ status,
-                                                                       Q4* __restrict__ scratch, const u32* __restrict__ gtab) {
+                                                                       Q4* __restrict__ scratch, const u32* __restrict__ gtab_g,
+                                                                       u32 smem_words) {
+    // secp256k1: the j*G half of the table is staged (the lambda*j*G half stays in L2); secp256r1: the whole table
+    const u32* gtab_s = stage_table(gtab_g, smem_words);
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     TabRef tab;
@@ -97,7 +113,7 @@ __global__ void __launch_bounds__(kBlock, SG_MINB_SW) ecrecover_kernel(const Q4*
         const int B = (int)((passes - pass) < (size_t)kSwBatch ? (passes - pass) : (size_t)kSwBatch);
         phase_sync<true>();
         io.first = pass * nthreads + gid;
-        sw_ecrecover_batch<C, kInnerSync>(B, io, tab, gtab);
+        sw_ecrecover_batch<C, kInnerSync>(B, io, tab, gtab_s, gtab_g);
     }
 }
 
@@ -141,7 +157,8 @@ struct EdDeviceIO {
 __global__ void __launch_bounds__(kBlock, SG_MINB_ED) ed25519_verify_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
                                                                             const Q4* __restrict__ pks, size_t n,
                                                                             uint8_t* __restrict__ valid, Q4* __restrict__ scratch,
-                                                                            const u32* __restrict__ btab) {
+                                                                            const u32* __restrict__ btab_g, u32 smem_words) {
+    const u32* btab = stage_table(btab_g, smem_words);
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     TabRef tab;
@@ -319,7 +336,7 @@ SG_HD void unit_double_mul(u32* out, const u32* u1, const u32* u2, const u32* xy
     F::from_plain(y, xy + 8);
     sw_build_table<C>(tab, x, y);
     JacPoint Q;
-    sw_double_mul<C, false>(Q, u1, u2, tab, gtab);
+    sw_double_mul<C, false>(Q, u1, u2, tab, gtab, gtab);
     for (int i = 0; i < 17; i++) out[i] = 0;
     if (Q.inf) {
         out[16] = 1;

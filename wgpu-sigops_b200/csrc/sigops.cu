@@ -62,6 +62,7 @@ struct Device {
     const u32 *k1g = nullptr, *r1g = nullptr, *edb = nullptr;
     int grid_k1 = 0, grid_r1 = 0, grid_ed = 0, grid_edm = 0, grid_unit = 0;
     float ms_h2d = 0, ms_kernel = 0, ms_d2h = 0;
+    bool smem_tables = true;  // SIGOPS_SMEM_TABLES=0 leaves the fixed-base tables in L2
 };
 
 std::vector<Device> g_dev;
@@ -128,6 +129,10 @@ int init_device(Device& d, int id) {
     d.k1g = k1t;
     d.r1g = r1t;
     d.edb = edt;
+    if (const char* e = getenv("SIGOPS_SMEM_TABLES")) d.smem_tables = atoi(e) != 0;
+    CK(cudaFuncSetAttribute(ecrecover_kernel<CurveK1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGTabEntries * 16 * 4));
+    CK(cudaFuncSetAttribute(ecrecover_kernel<CurveR1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGTabEntries * 16 * 4));
+    CK(cudaFuncSetAttribute(ed25519_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGTabEntries * 24 * 4));
     if (max_grid(d, ecrecover_kernel<CurveK1>, &d.grid_k1)) return 1;
     if (max_grid(d, ecrecover_kernel<CurveR1>, &d.grid_r1)) return 1;
     if (max_grid(d, ed25519_verify_kernel, &d.grid_ed)) return 1;
@@ -199,18 +204,21 @@ int launch_op(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_msgs, co
     int grid = (int)std::min<size_t>(blocks, (size_t)max_g);
     size_t chunks = op == OP_ED ? kEdBatchChunks : kSwBatchChunks;
     if (ensure_scratch(d, chunks * (size_t)max_g * kBlock)) return 1;
+    // stage the fixed-base table in shared memory when the launch is big enough to amortise the copy (>= 1 full pass)
+    const bool stage = d.smem_tables && n >= (size_t)d.sms * kBlock && tpb == kBlock;
+    const u32 sw_words = stage ? (u32)kGTabEntries * 16 : 0, ed_words = stage ? (u32)kGTabEntries * 24 : 0;
     switch (op) {
         case OP_K1:
-            ecrecover_kernel<CurveK1><<<grid, tpb, 0, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, n, (Q4*)d_out,
-                                                            d_status, d.scratch, d.k1g);
+            ecrecover_kernel<CurveK1><<<grid, tpb, sw_words * 4, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, n, (Q4*)d_out,
+                                                                       d_status, d.scratch, d.k1g, sw_words);
             break;
         case OP_R1:
-            ecrecover_kernel<CurveR1><<<grid, tpb, 0, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, n, (Q4*)d_out,
-                                                            d_status, d.scratch, d.r1g);
+            ecrecover_kernel<CurveR1><<<grid, tpb, sw_words * 4, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, n, (Q4*)d_out,
+                                                                       d_status, d.scratch, d.r1g, sw_words);
             break;
         case OP_ED:
-            ed25519_verify_kernel<<<grid, tpb, 0, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, (const Q4*)d_pks, n,
-                                                         d_out, d.scratch, d.edb);
+            ed25519_verify_kernel<<<grid, tpb, ed_words * 4, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, (const Q4*)d_pks, n,
+                                                                   d_out, d.scratch, d.edb, ed_words);
             break;
     }
     CK(cudaGetLastError());
