@@ -413,6 +413,11 @@ SG_HD bool ed_verify_point(EdPoint& acc, const u32* sig_w, const u32* pk_w, cons
 #else
     typedef Fp25519 FH;
 #endif
+#if defined(SG_HOT_DBL_ONLY)
+    typedef Fp25519 FHA;
+#else
+    typedef FH FHA;
+#endif
     phase_sync<kSync>();
     // No early exit (every thread of the block must reach every phase barrier): a key that does not decompress or a
     // non-canonical s keeps walking the program on whatever values it has and the verdict is forced to 0 at the end.
@@ -480,11 +485,16 @@ SG_HD bool ed_verify_point(EdPoint& acc, const u32* sig_w, const u32* pk_w, cons
         phase_sync<kSync>();
         if (i != 63) {
 #pragma unroll 1
-            for (int d = 0; d < 4; d++) ed_dbl<FH>(acc, d == 3);
+            for (int d = 0; d < 4; d++) {
+#if defined(SG_SYNC_DBL)
+                phase_sync<kSync>();
+#endif
+                ed_dbl<FH>(acc, d == 3);
+            }
         }
-        ed_add_from_table<FH>(acc, tab, recode_digit<4>(kp[0], i), true);
+        ed_add_from_table<FHA>(acc, tab, recode_digit<4>(kp[0], i), true);
         if (gcount == 0) {
-            ed_add_from_btab<FH>(acc, btab, recode_digit<kGWin>(kp[1], (i * 43) >> 7 /* i / 3 */), true);
+            ed_add_from_btab<FHA>(acc, btab, recode_digit<kGWin>(kp[1], (i * 43) >> 7 /* i / 3 */), true);
             gcount = 2;
         } else {
             gcount--;

@@ -435,6 +435,11 @@ SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabR
                          const u32* gtab_global) {
     // gtab: the j*G table (possibly the shared-memory copy); gtab_global: the full table in global memory, whose second
     // half holds lambda*j*G for secp256k1
+#if defined(SG_HOT_DBL_ONLY)
+    typedef typename C::Cold HA;  // additions with out-of-line products, doublings inlined
+#else
+    typedef typename C::Hot HA;
+#endif
     typedef typename C::Hot H;
     acc.inf = true;
     C::F::set_zero(acc.X);
@@ -465,16 +470,21 @@ SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabR
             phase_sync<kSync>();
             if (i != 32) {
 #pragma unroll 1
-                for (int d = 0; d < 4; d++) jac_dbl<H>(acc);
+                for (int d = 0; d < 4; d++) {
+#if defined(SG_SYNC_DBL)
+                    phase_sync<kSync>();
+#endif
+                    jac_dbl<H>(acc);
+                }
             }
 #pragma unroll 1
-            for (int s = 0; s < 2; s++) sw_add_from_table<H>(acc, tab, recode_digit<4>(kp[s], i), flip[s], s == 1);
+            for (int s = 0; s < 2; s++) sw_add_from_table<HA>(acc, tab, recode_digit<4>(kp[s], i), flip[s], s == 1);
             // i = 30, 27, ..., 0  <->  G window i / 3 = 10 ... 0   (i = 32, 31 carry no G window)
             if (i <= 30) {
                 if (gcount == 0) {
 #pragma unroll 1
                     for (int s = 2; s < 4; s++)
-                        sw_add_from_gtab<H>(acc, s == 3 ? gtab_global + kGTabEntries * 16 : gtab,
+                        sw_add_from_gtab<HA>(acc, s == 3 ? gtab_global + kGTabEntries * 16 : gtab,
                                             recode_digit<kGWin>(kp[s], (i * 11) >> 5 /* i / 3 for i <= 30 */), flip[s]);
                     gcount = 2;
                 } else {
@@ -499,13 +509,18 @@ SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabR
             phase_sync<kSync>();
             if (i != 64) {
 #pragma unroll 1
-                for (int d = 0; d < 4; d++) jac_dbl<H>(acc);
+                for (int d = 0; d < 4; d++) {
+#if defined(SG_SYNC_DBL)
+                    phase_sync<kSync>();
+#endif
+                    jac_dbl<H>(acc);
+                }
             }
-            sw_add_from_table<H>(acc, tab, recode_digit<4>(kp[0], i), false, false);
+            sw_add_from_table<HA>(acc, tab, recode_digit<4>(kp[0], i), false, false);
             // i = 63, 60, ..., 0  <->  G window i / 3 = 21 ... 0
             if (i <= 63) {
                 if (gcount == 0) {
-                    sw_add_from_gtab<H>(acc, gtab, recode_digit<kGWin>(kp[1], (i * 43) >> 7 /* i / 3 for i < 128 */), false);
+                    sw_add_from_gtab<HA>(acc, gtab, recode_digit<kGWin>(kp[1], (i * 43) >> 7 /* i / 3 for i < 128 */), false);
                     gcount = 2;
                 } else {
                     gcount--;
