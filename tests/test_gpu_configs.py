@@ -97,3 +97,39 @@ def test_sub_shards_cover_large_batches(sigops, monkeypatch):
     assert (out == pk).all() and (got == st).all()
     s2, m2, p2, v, _ = batches.ed25519_batch(23456, edge_every=9, seed=42)
     assert (sigops.ed25519_eddsa.ecverify_array(s2, m2, p2) == v).all()
+
+
+def test_concurrent_callers_are_serialised(sigops):
+    """The entry points are blocking and thread-safe (one internal lock): four threads calling different operations at
+    once all get the right answers (the reference serialises its GPU tests with serial_test instead,
+    src/tests/secp256k1_ecdsa.rs:11-13)."""
+    import threading
+
+    k1 = batches.ecdsa_batch(0, 20011, edge_every=101, seed=51)
+    r1 = batches.ecdsa_batch(1, 15013, edge_every=103, seed=52)
+    ed = batches.ed25519_batch(17017, edge_every=7, seed=53)
+    errors = []
+
+    def run_k1():
+        for _ in range(3):
+            out, st = sigops.secp256k1_ecdsa.ecrecover_with_status(k1[0], k1[1])
+            if not ((out == k1[2]).all() and (st == k1[3]).all()):
+                errors.append("k1")
+
+    def run_r1():
+        for _ in range(3):
+            out, st = sigops.secp256r1_ecdsa.ecrecover_with_status(r1[0], r1[1])
+            if not ((out == r1[2]).all() and (st == r1[3]).all()):
+                errors.append("r1")
+
+    def run_ed():
+        for _ in range(3):
+            if not (sigops.ed25519_eddsa.ecverify_array(ed[0], ed[1], ed[2]) == ed[3]).all():
+                errors.append("ed")
+
+    threads = [threading.Thread(target=f) for f in (run_k1, run_r1, run_ed, run_k1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
