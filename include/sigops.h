@@ -107,8 +107,10 @@ int sigops_precompute_bases(int curve, uint32_t log_limb_size, uint32_t* out, si
  * (src/benchmarks/mod.rs:10-53).  bounds must hold n_devices + 1 entries. */
 int sigops_plan_shards(size_t n, int n_devices, size_t* bounds, int* n_used);
 
-/* Observability (the reference has none: `timestamp_writes: None`, src/gpu.rs:98).  Milliseconds of the
- * last host-buffer call, measured with CUDA events on each device's stream; max over the devices used. */
+/* Observability (the reference has none: `timestamp_writes: None`, src/gpu.rs:98).  Milliseconds of the last
+ * host-buffer call, measured with CUDA events; max over the devices used.  A shard flows through an upload / kernel /
+ * download pipeline in pieces, so: h2d = the first piece's upload (what is exposed before the first kernel), kernel = first
+ * kernel start to last kernel end (the other uploads and downloads overlap it), d2h = what remains after the last kernel. */
 int sigops_last_timing(double* h2d_ms, double* kernel_ms, double* d2h_ms);
 /* Number of kernels the engine has launched in this process (all devices). */
 uint64_t sigops_kernel_launches(void);
