@@ -278,6 +278,53 @@ SG_HD u32 mad_row1(u32* acc, u32 x0, u32 b) {
     return c;
 }
 
+// acc[0..8) += {x0..x3} * b on aligned pairs, and the chain continues into a FRESH pair: (acc[8], acc[9]) = x4 * b2 + carry.
+// Appending the next row's top product to this row's chain means the carry out of the chain never has to be
+// materialised in a register pair of its own (a SEL plus a zeroing IMAD.MOV on the multiplier pipe per row).
+SG_HD void mad_row5(u32* acc, u32 x0, u32 x1, u32 x2, u32 x3, u32 b, u32 x4, u32 b2) {
+#if SG_PTX
+    asm("mad.lo.cc.u32 %0, %10, %14, %0;\n\t"
+        "madc.hi.cc.u32 %1, %10, %14, %1;\n\t"
+        "madc.lo.cc.u32 %2, %11, %14, %2;\n\t"
+        "madc.hi.cc.u32 %3, %11, %14, %3;\n\t"
+        "madc.lo.cc.u32 %4, %12, %14, %4;\n\t"
+        "madc.hi.cc.u32 %5, %12, %14, %5;\n\t"
+        "madc.lo.cc.u32 %6, %13, %14, %6;\n\t"
+        "madc.hi.cc.u32 %7, %13, %14, %7;\n\t"
+        "madc.lo.cc.u32 %8, %15, %16, 0;\n\t"
+        "madc.hi.u32 %9, %15, %16, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
+          "=r"(acc[8]), "=r"(acc[9])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b), "r"(x4), "r"(b2));
+#else
+    u32 c = mad_row4(acc, x0, x1, x2, x3, b);
+    u64 p = (u64)x4 * b2 + c;
+    acc[8] = (u32)p;
+    acc[9] = (u32)(p >> 32);
+#endif
+}
+
+// acc[0..6) += {x0,x1,x2} * b on aligned pairs; the carry is propagated into the live pair (acc[6], acc[7])
+SG_HD void mad_row3c(u32* acc, u32 x0, u32 x1, u32 x2, u32 b) {
+#if SG_PTX
+    asm("mad.lo.cc.u32 %0, %8, %11, %0;\n\t"
+        "madc.hi.cc.u32 %1, %8, %11, %1;\n\t"
+        "madc.lo.cc.u32 %2, %9, %11, %2;\n\t"
+        "madc.hi.cc.u32 %3, %9, %11, %3;\n\t"
+        "madc.lo.cc.u32 %4, %10, %11, %4;\n\t"
+        "madc.hi.cc.u32 %5, %10, %11, %5;\n\t"
+        "addc.cc.u32 %6, %6, 0;\n\t"
+        "addc.u32 %7, %7, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(b));
+#else
+    u32 c = mad_row3(acc, x0, x1, x2, b);
+    u64 t = (((u64)acc[7] << 32) | acc[6]) + c;
+    acc[6] = (u32)t;
+    acc[7] = (u32)(t >> 32);
+#endif
+}
+
 // (lo,hi) = x*b written to acc[0],acc[1] (no accumulate)
 SG_HD void mul_wide(u32* acc, u32 x, u32 b) {
 #if SG_PTX
@@ -325,8 +372,11 @@ SG_HD void merge_even_odd(u32* r, const u32* e, const u32* o) {
 #endif
 }
 
-// r[0..16) = a[0..8) * b[0..8): 64 wide MACs on even/odd column accumulators (carry-outs always land on a
-// fresh limb, see DESIGN.md "field multiplication").
+// r[0..16) = a[0..8) * b[0..8): 64 wide MACs on even/odd column accumulators (e: products a_i*b_j with i+j even at limb
+// i+j; o: i+j odd at limb i+j-1; result = e + (o << 32)).  Row j adds a*b_j; a row whose chain ends on a live limb takes
+// the NEXT row's top product a7*b_(j+1) -- which lands on the fresh pair just above -- as a fifth element, and that next
+// row then runs three products plus a two-limb carry propagation (mad_row5 / mad_row3c): no carry limb is ever
+// materialised except the final o[14].
 SG_HD void mul8x8(u32* r, const u32* a, const u32* b) {
     u32 e[16], o[16];
 #pragma unroll
@@ -343,19 +393,35 @@ SG_HD void mul8x8(u32* r, const u32* a, const u32* b) {
     mul_wide(o + 2, a[3], b[0]);
     mul_wide(o + 4, a[5], b[0]);
     mul_wide(o + 6, a[7], b[0]);
+#if defined(SG_MUL_CARRY_LIMBS)
 #pragma unroll
     for (int i = 1; i < 8; i += 2) {
-        // odd row i: a_even*b_i -> odd columns (o index i-1..i+6, second use: carry to fresh o[i+7]);
-        //            a_odd*b_i  -> even columns (e index i+1..i+8, top pair fresh)
         o[i + 7] = mad_row4(o + i - 1, a[0], a[2], a[4], a[6], b[i]);
         mad_row4(e + i + 1, a[1], a[3], a[5], a[7], b[i]);
         if (i + 1 < 8) {
-            // even row i+1: a_even*b -> even columns (e index i+1..i+8, second use: carry to fresh e[i+9]);
-            //               a_odd*b  -> odd columns (o index i+1..i+8, top pair holds only the carry limb)
             e[i + 9] = mad_row4(e + i + 1, a[0], a[2], a[4], a[6], b[i + 1]);
             mad_row4(o + i + 1, a[1], a[3], a[5], a[7], b[i + 1]);
         }
     }
+#else
+    // row 1: o[0..8) += a_even*b1, then (o8,o9) = a7*b2 + carry;  e[2..10) += a_odd*b1 (top pair fresh: no carry out)
+    mad_row5(o + 0, a[0], a[2], a[4], a[6], b[1], a[7], b[2]);
+    mad_row4(e + 2, a[1], a[3], a[5], a[7], b[1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+        // even row j: e[j..j+8) += a_even*b_j, then (e[j+8], e[j+9]) = a7*b_(j+1) + carry;
+        //             o[j..j+6) += a1,a3,a5 * b_j, carry into the live pair (o[j+6], o[j+7]) = a7*b_j (+ earlier carry)
+        mad_row5(e + j, a[0], a[2], a[4], a[6], b[j], a[7], b[j + 1]);
+        mad_row3c(o + j, a[1], a[3], a[5], b[j]);
+        // odd row j+1: e[j+2..j+8) += a1,a3,a5 * b_(j+1), carry into the live pair (e[j+8], e[j+9]);
+        //              o[j..j+8) += a_even*b_(j+1), then (o[j+8], o[j+9]) = a7*b_(j+2) + carry (last row: carry -> o[14])
+        mad_row3c(e + j + 2, a[1], a[3], a[5], b[j + 1]);
+        if (j + 2 < 8)
+            mad_row5(o + j, a[0], a[2], a[4], a[6], b[j + 1], a[7], b[j + 2]);
+        else
+            o[14] = mad_row4(o + j, a[0], a[2], a[4], a[6], b[j + 1]);
+    }
+#endif
     merge_even_odd(r, e, o);
 }
 
