@@ -170,7 +170,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "sigs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "curves": extra, "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(json.dumps(line))
     return 0
 
 
@@ -476,7 +476,7 @@ def run_sigops(args):
             "gpu_launches": int(launches_timed), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "curves": results, "extensions": ext,
         }
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -521,7 +521,33 @@ def _hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+class _StdoutGuard:
+    """Keeps stdout for the ONE JSON line: file descriptor 1 is pointed at stderr while the benchmark runs (NCCL prints a
+    version banner on stdout at the first collective), and the saved descriptor is used for the final line."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.saved, (line + "\n").encode())
+
+
+_guard = None
+
+
+def emit(line: str):
+    if _guard is not None:
+        _guard.emit(line)
+    else:
+        print(line, flush=True)
+
+
 def main():
+    global _guard
+    _guard = _StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
