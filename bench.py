@@ -42,6 +42,10 @@ import numpy as np  # noqa: E402
 BATCH = 1 << 20
 # algorithmic work per signature in IMAD-equivalents (2 x 32x32->64 limb-MACs)
 IMAD_EQ = {"secp256k1": 451_616, "secp256r1": 554_784, "ed25519": 461_400}
+# Wide MACs (IMAD.WIDE.U32[.X]) actually executed per signature, from the ncu source page of the committed capture
+# (profiles/r01_ncu_instruction_mix.txt); x2 = IMAD-equivalents.  Reported next to the contract figure so that a
+# contract-based fraction above 1.0 can be read against what the multiplier pipe really did.
+EXECUTED_WIDE_MACS = {"secp256k1": 133_229, "secp256r1": 165_708, "ed25519": 167_901}
 # HBM bytes per signature (inputs + outputs incl. the status byte)
 HBM_BYTES = {"secp256k1": 96 + 65, "secp256r1": 96 + 65, "ed25519": 128 + 1}
 CURVES = ("secp256k1", "secp256r1", "ed25519")
@@ -337,6 +341,8 @@ def run_sigops(args):
                     "last_call_ms": {"h2d": h2d.value, "kernel": ker.value, "d2h": d2h.value}},
             "roofline": {"bound": "int32_imad", "achieved": achieved / 1e9, "peak": imad_peak / 1e9, "unit": "GIMAD/s",
                          "frac": achieved / imad_peak, "imad_eq_per_sig": IMAD_EQ[curve],
+                         "executed_imad_eq_per_sig": 2 * EXECUTED_WIDE_MACS[curve],
+                         "executed_frac": val / world * 2 * EXECUTED_WIDE_MACS[curve] / imad_peak,
                          "hbm_frac": (val / world * HBM_BYTES[curve] / 1e9) / _hbm_peak()[0]},
             "parity": "bit-exact vs generator-expected outputs (all %d rows)" % n,
         }
@@ -463,7 +469,9 @@ def run_sigops(args):
                      "peak_source": "live sigops_imad_peak(kind 0: independent mad.lo.u32 chains, full occupancy) "
                                     "on this GPU in this run; MEASURED_PEAKS.json has no INT32 entry",
                      "imad_wide_peak": imad_wide_peak / 1e9, "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
-                     "note": "bound is the INT32 multiply pipe (north_star), not HBM/tensor; hbm_frac shown for scale"})
+                     "note": "bound is the INT32 multiply pipe (north_star), not HBM/tensor; hbm_frac shown for scale. frac uses "
+                             "the contract's algorithmic work (SURVEY.md 8d: squarings charged as products, Fermat inversions, "
+                             "wNAF tables) and can exceed 1; executed_frac uses the wide MACs the kernel really issues (ncu)"})
         line = {
             "metric": METRIC, "value": head["value"], "unit": "sigs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
