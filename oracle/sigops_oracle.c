@@ -23,7 +23,8 @@
  * PARITY PINNING: this file is pinned to oracle/sigops_oracle.py on every edge class and on random inputs
  * (tests/test_oracle.py), and the Python oracle is pinned to the reference's golden vectors, RFC 8032 vectors and
  * OpenSSL (see its header).  Rejecting outcomes are "parity unpinned" with respect to the reference itself (no Rust
- * toolchain in this image; the reference never tests them).
+ * toolchain in this image; the reference never tests them); they are cross-checked against OpenSSL (Ed25519 verify,
+ * ECDSA verify of every recovered key) and libsodium (strict mode) on the whole edge corpus, through this file too.
  *
  * Arithmetic: 4 x 64-bit limbs, generic Montgomery multiplication (unsigned __int128) for all six moduli.
  */

@@ -40,7 +40,14 @@ non-canonical s/A/R, small-order points) -- the reference never tests them
 (SURVEY.md section 4); for those this oracle follows the published algorithms of the
 pinned third-party versions named above.  The Rust toolchain is absent from this
 image, so the reference itself cannot be run here ("parity unpinned" for the
-rejecting classes).
+rejecting classes with respect to fuel-crypto / ed25519-dalek themselves).  Those classes
+are cross-checked against two independent production implementations of the same
+published decision procedures instead: OpenSSL's Ed25519 verify (cofactorless, s < L,
+no y < p check, bytewise R compare = dalek `verify`) and ECDSA verify (every recovered
+key must verify, every range rejection must fail) in tests/test_oracle.py
+(`test_openssl_pins_*`), and libsodium for `verify_strict`
+(tests/test_ed25519_strict.py::test_libsodium_pins_strict_verdicts): full agreement on
+every edge class of the corpus.
 """
 from __future__ import annotations
 

@@ -59,6 +59,32 @@ def _blob(cs):
     return b"".join(c[2] for c in cs) or b"\0", offs
 
 
+def test_libsodium_pins_strict_verdicts():
+    """`verify_strict` against an independent implementation: libsodium's `crypto_sign_open` (via PyNaCl) rejects
+    small-order A and R and non-canonical s / A / R -- on every constructible class that is dalek 2.1.1
+    `verify_strict`'s decision (a non-canonical A of large order would differ, but nobody can sign under one).  The whole
+    strict corpus, variable-length messages included: Python oracle == C oracle == libsodium."""
+    nb = pytest.importorskip("nacl.bindings")
+    import nacl.exceptions
+
+    def sodium(sig, msg, pk):
+        try:
+            nb.crypto_sign_open(sig + msg, pk)
+            return True
+        except nacl.exceptions.BadSignatureError:
+            return False
+
+    cs = strict_cases.cases()
+    got_c = coracle.ecverify_ed25519_msgs([c[1] for c in cs], [c[2] for c in cs], [c[3] for c in cs], strict=True)
+    n_flip = 0
+    for (name, sg, m, pk), gc in zip(cs, got_c):
+        want = sodium(sg, m, pk)
+        assert o.ecverify_ed25519_strict(sg, m, pk) == want, name
+        assert bool(gc) == want, name
+        n_flip += (len(m) == 32 and o.ecverify_ed25519(sg, m, pk) != want)
+    assert n_flip >= 10  # the classes where strict and non-strict differ are all there
+
+
 def test_hostsim_matches_oracle():
     lib = load_hostsim()
     cs = strict_cases.cases()

@@ -7,7 +7,8 @@
 3. the committed fixtures under tests/golden/ against both.
 
 The reference itself (Rust) cannot be executed in this image, so rejecting outcomes are pinned only to the published
-algorithms of the pinned third-party versions ("parity unpinned" for those classes; see the oracle header).
+algorithms of the pinned third-party versions ("parity unpinned" for those classes; see the oracle header) and, as
+an independent check, to OpenSSL's verdicts on the whole edge corpus (`test_openssl_pins_*`).
 """
 import hashlib
 import json
@@ -168,6 +169,81 @@ def test_openssl_cross_check():
     sigs, msgs, pks = coracle.gen_ed25519(16, seed=99)
     for sg, m, pk in zip(sigs, msgs, pks):
         ed25519.Ed25519PublicKey.from_public_bytes(pk.tobytes()).verify(sg.tobytes(), m.tobytes())
+
+
+def test_openssl_pins_ed25519_edge_classes():
+    """Every Ed25519 edge class of the corpus (all the REJECTING outcomes, and the surprising accepts: small-order and
+    non-canonical A with a crafted R, x = 0 with the sign bit set) against an independent production implementation:
+    OpenSSL's Ed25519 verify is cofactorless, checks s < L, does not check y < p and compares R bytewise -- the
+    decision procedure of ed25519-dalek 2.1.1 `verify`.  Oracle (Python and C) == OpenSSL on all of them."""
+    from cryptography.exceptions import InvalidSignature
+    from cryptography.hazmat.primitives.asymmetric import ed25519
+
+    def openssl_verify(sig, msg, pk):
+        try:
+            ed25519.Ed25519PublicKey.from_public_bytes(pk).verify(sig, msg)
+            return True
+        except InvalidSignature:
+            return False
+
+    corpus = o.ed25519_edge_cases()
+    assert len(corpus) > 70
+    n_reject = 0
+    for name, sg, m, pk in corpus:
+        want = openssl_verify(sg, m, pk)
+        assert o.ecverify_ed25519(sg, m, pk) == want, name
+        assert bool(coracle.ecverify_ed25519([sg], [m], [pk])[0]) == want, name
+        if want:  # strict may only ever be stricter
+            assert o.ecverify_ed25519(sg, m, pk)
+        else:
+            assert not o.ecverify_ed25519_strict(sg, m, pk), name
+            n_reject += 1
+    assert n_reject > 50
+    # random corruptions of valid signatures (bit flips in R, s, A, M): 400 rows, same verdicts
+    sigs, msgs, pks = coracle.gen_ed25519(400, seed=7)
+    rng = random.Random(7)
+    for i in range(400):
+        arr = (sigs, sigs, pks, msgs)[i % 4]
+        col = rng.randrange(32) + (32 if i % 4 == 1 else 0)
+        arr[i, col] ^= 1 << rng.randrange(8)
+    got = coracle.ecverify_ed25519(sigs, msgs, pks)
+    for i in range(400):
+        assert bool(got[i]) == openssl_verify(sigs[i].tobytes(), msgs[i].tobytes(), pks[i].tobytes()), i
+
+
+def test_openssl_pins_ecdsa_edge_classes():
+    """ECDSA edge corpus against OpenSSL: whenever the oracle recovers a key, (r, s) must VERIFY under that key in OpenSSL
+    (high-s, z >= n, z = 0, R = +-G, the doubling corner cases included -- OpenSSL has no low-s rule either); whenever
+    the oracle rejects for range reasons (r or s zero, r >= n) OpenSSL rejects the signature under any key (checked with
+    G); a recovered key for the other parity is a different key that verifies too."""
+    from cryptography.exceptions import InvalidSignature
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric import ec, utils
+
+    for c, cid, curve in ((o.K1, 0, ec.SECP256K1()), (o.R1, 1, ec.SECP256R1())):
+        g_pub = ec.EllipticCurvePublicNumbers(c.gx, c.gy, curve).public_key()
+        n_rec = n_rej = 0
+        for name, sg, m in o.ecdsa_edge_cases(c):
+            got = o.ecrecover(c, sg, m)
+            cg, cst = coracle.ecrecover(cid, [sg], [m])
+            assert (cst[0] == 0) == (got is not None), name
+            r = int.from_bytes(sg[:32], "big")
+            s = int.from_bytes(bytes([sg[32] & 0x7F]) + sg[33:], "big")
+            if got is not None:
+                assert cg[0].tobytes() == got, name
+                pub = ec.EllipticCurvePublicNumbers(
+                    int.from_bytes(got[:32], "big"), int.from_bytes(got[32:], "big"), curve).public_key()
+                n_rec += 1
+            else:
+                pub = g_pub
+                n_rej += 1
+            try:
+                pub.verify(utils.encode_dss_signature(r, s), m, ec.ECDSA(utils.Prehashed(hashes.SHA256())))
+                ok = True
+            except InvalidSignature:
+                ok = False
+            assert ok == (got is not None), name
+        assert n_rec >= 10 and n_rej >= 8
 
 
 # ---------------------------------------------------------------------------------------- C oracle == Python oracle
