@@ -130,6 +130,55 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
+# ------------------------------------------------------------------------------------------------ streaming service mode
+def queue_throughput(w, curve: str, req_n: int, depth: int, n_requests: int, pool, seed: int = 0x51600002):
+    """`n_requests` requests of `req_n` signatures through a `service.SigQueue` with `depth` of them in
+    flight (host pinned slot arrays -> H2D -> fused kernel -> D2H inside the timed region; every result compared with the
+    expected values).  pool = (sigs, msgs, pks_or_None, expected) of at least req_n rows.  Returns a dict."""
+    sigs, msgs, pks, exp = pool
+    n_pool = sigs.shape[0]
+    starts = [(i * req_n) % max(1, n_pool - req_n + 1) for i in range(n_requests)]
+    lat = []
+    bad = 0
+    with w.service.SigQueue(curve, req_n, depth) as q:
+        def fill(slot, a):
+            q.sigs(slot)[:req_n] = sigs[a:a + req_n]
+            q.msgs(slot)[:req_n] = msgs[a:a + req_n]
+            if pks is not None:
+                q.pks(slot)[:req_n] = pks[a:a + req_n]
+
+        for slot in range(depth):  # warm-up: one request per slot (captures the slot's graph)
+            fill(slot, 0)
+            q.submit(slot, req_n)
+        for slot in range(depth):
+            q.wait(slot)
+        t_sub = [0.0] * depth
+        where = [0] * depth
+        t0 = time.perf_counter()
+        for i in range(n_requests + depth):
+            slot = i % depth
+            if i >= depth:
+                out, st = q.wait(slot)
+                lat.append(time.perf_counter() - t_sub[slot])
+                a = where[slot]
+                ok = np.array_equal(out.reshape(exp[a:a + req_n].shape), exp[a:a + req_n]) and (st is None or not st.any())
+                bad += not ok
+            if i < n_requests:
+                fill(slot, starts[i])
+                where[slot] = starts[i]
+                t_sub[slot] = time.perf_counter()
+                q.submit(slot, req_n)
+        dt = time.perf_counter() - t0
+        info = q.info()
+    if bad:
+        raise SystemExit(f"queue({curve}, depth {depth}): {bad} requests differ from the expected values -- refusing to report")
+    lat.sort()
+    return {"depth": depth, "request_sigs": req_n, "requests": n_requests, "sigs_per_s": n_requests * req_n / dt,
+            "requests_per_s": n_requests / dt, "latency_ms_p50": lat[len(lat) // 2] * 1e3,
+            "latency_ms_p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))] * 1e3,
+            "graph_launches": info["graph_launches"], "graph_captures": info["graph_captures"]}
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
     """The reference's CPU path for this metric, timed on the host cores.  The Rust reference (fuel-crypto /
@@ -428,6 +477,19 @@ def run_sigops(args):
         for ptr in (p_s, p_m, p_o, p_a, p_k, p_t):
             lib.sigops_host_free(ptr)
         log(f"[rank 0] k1 raw->address: {n / (ker.value * 1e-3) / 1e6:.2f} M sigs/s kernels, {n * args.steps / dt / 1e6:.2f} M sigs/s e2e")
+
+    # ---- extension row: streaming service mode -- 1,024-signature secp256k1 requests through a
+    #      sigops_queue, 1 / 4 / 16 in flight (pinned slot arrays, one CUDA graph per request) ----
+    if rank == 0 and world == 1 and (args.curves == "all" or "secp256k1" in args.curves):
+        pool = make_batch("secp256k1", 1 << 16, 1 << 16, 0x51600003, host_threads)
+        rows = [queue_throughput(w, "secp256k1", 1024, d, 64 * d if d > 1 else 100, pool) for d in (1, 4, 16)]
+        ext = ext or {}
+        ext["secp256k1_queue_1024"] = {
+            "rows": rows, "unit": "sigs/s",
+            "note": "service.SigQueue / sigops_queue_*: requests of 1,024 signatures, host time from submit to wait per "
+                    "request, H2D + kernel + D2H inside; depth = requests in flight on one GPU"}
+        log("[rank 0] k1 queue, 1024-signature requests: " + ", ".join(
+            f"depth {r['depth']}: {r['sigs_per_s'] / 1e6:.2f} M sigs/s (p50 {r['latency_ms_p50']:.2f} ms)" for r in rows))
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None

@@ -120,6 +120,35 @@ uint64_t sigops_kernel_launches(void);
 void* sigops_host_alloc(size_t bytes);
 void sigops_host_free(void* p);
 
+/* Streaming service mode: a persistent ring of pre-registered pinned buffers instead of one
+ * blocking call per batch.  Replaces, for a long-running verifier, the per-call device creation, buffer allocation and
+ * blocking `device.poll(Maintain::Wait)` of src/gpu.rs:5-35,129-170.
+ * A queue serves ONE operation (SIGOPS_CURVE_*) on ONE device of the pool (device_index = index into the pool, not a CUDA
+ * ordinal) with `depth` slots of up to `max_batch` signatures each.  Every slot owns pinned host input / output arrays,
+ * device buffers, scratch and a CUDA stream; a slot's upload, fused kernel and download are replayed as one CUDA graph
+ * while the request size repeats.  Slots in flight run concurrently on the device: small requests (a few thousand
+ * signatures use one or two of the 16 resident warps per SM) overlap, so throughput scales with the number of slots in
+ * flight at the latency of a single request.
+ * Life cycle of a slot: write the inputs into the arrays sigops_queue_buffers() returns (layouts as in the blocking entry
+ * points; `pks` is NULL unless the queue is ed25519; `status` is NULL for ed25519) -> sigops_queue_submit(slot, n)
+ * (asynchronous; fails if the slot is still in flight or n > max_batch) -> sigops_queue_wait(slot) (blocks until that
+ * request has completed) -> read `out` / `status` -> reuse the slot.  sigops_queue_poll() is the non-blocking test.
+ * Thread-safe: several threads may drive different slots of one queue.  All queues must be destroyed before
+ * sigops_shutdown().  SIGOPS_QUEUE_GRAPHS=0 disables graph replay (plain stream launches). */
+typedef struct sigops_queue sigops_queue;
+#define SIGOPS_QUEUE_MAX_DEPTH 64
+int sigops_queue_create(int curve, int device_index, size_t max_batch, int depth, sigops_queue** out);
+int sigops_queue_destroy(sigops_queue* q);
+int sigops_queue_buffers(sigops_queue* q, int slot, uint8_t** sigs, uint8_t** msgs, uint8_t** pks, uint8_t** out,
+                         uint8_t** status);
+int sigops_queue_submit(sigops_queue* q, int slot, size_t n);
+int sigops_queue_poll(sigops_queue* q, int slot, int* done);
+/* n_done (may be NULL): size of the request that completed; device_ms (may be NULL): upload + kernel + download time of
+ * that request on the device (CUDA events). */
+int sigops_queue_wait(sigops_queue* q, int slot, size_t* n_done, double* device_ms);
+int sigops_queue_info(sigops_queue* q, int* curve, int* device_index, size_t* max_batch, int* depth,
+                      uint64_t* graph_launches, uint64_t* graph_captures);
+
 /* Device-resident variants: inputs and outputs already live in the CURRENT CUDA device's memory
  * (16-byte aligned); the kernel is enqueued on `cuda_stream` (a cudaStream_t; NULL = default stream) and the
  * call returns without synchronising.  Used by bench.py for the kernel-only figure. */

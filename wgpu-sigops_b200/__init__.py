@@ -11,5 +11,5 @@ Module and function names follow the reference crate so the parity tests read li
 The package directory is named `wgpu-sigops_b200`; import it as `wgpu_sigops_b200` (see the loader module of that
 name at the repository root).
 """
-from . import ed25519_eddsa, pipeline, precompute, secp256k1_ecdsa, secp256r1_ecdsa  # noqa: F401
+from . import ed25519_eddsa, pipeline, precompute, secp256k1_ecdsa, secp256r1_ecdsa, service  # noqa: F401
 from ._lib import ShaderFailureError, load  # noqa: F401

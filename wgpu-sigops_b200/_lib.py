@@ -19,6 +19,8 @@ SYMBOLS = [
     "sigops_secp256k1_ecrecover_device", "sigops_secp256r1_ecrecover_device", "sigops_ed25519_ecverify_device",
     "sigops_test_unit", "sigops_test_unit_shape", "sigops_imad_peak", "sigops_plan_shards",
     "sigops_ed25519_ecverify_msgs", "sigops_sha256_batch", "sigops_ecrecover_addresses",
+    "sigops_queue_create", "sigops_queue_destroy", "sigops_queue_buffers", "sigops_queue_submit", "sigops_queue_poll",
+    "sigops_queue_wait", "sigops_queue_info",
 ]
 
 _lib = None
@@ -62,6 +64,15 @@ def load() -> ctypes.CDLL:
     lib.sigops_test_unit_shape.argtypes = [i32, c.POINTER(i32), c.POINTER(i32)]
     lib.sigops_plan_shards.argtypes = [sz, i32, c.POINTER(sz), c.POINTER(i32)]
     lib.sigops_imad_peak.argtypes = [i32, i32, c.POINTER(c.c_double), c.POINTER(c.c_double)]
+    pvp = c.POINTER(vp)
+    lib.sigops_queue_create.argtypes = [i32, i32, sz, i32, pvp]
+    lib.sigops_queue_destroy.argtypes = [vp]
+    lib.sigops_queue_buffers.argtypes = [vp, i32, pvp, pvp, pvp, pvp, pvp]
+    lib.sigops_queue_submit.argtypes = [vp, i32, sz]
+    lib.sigops_queue_poll.argtypes = [vp, i32, c.POINTER(i32)]
+    lib.sigops_queue_wait.argtypes = [vp, i32, c.POINTER(sz), c.POINTER(c.c_double)]
+    lib.sigops_queue_info.argtypes = [vp, c.POINTER(i32), c.POINTER(i32), c.POINTER(sz), c.POINTER(i32),
+                                      c.POINTER(c.c_uint64), c.POINTER(c.c_uint64)]
     _lib = lib
     return lib
 

@@ -29,6 +29,7 @@ std::mutex g_mu;      // serialises the entry points
 std::mutex g_err_mu;  // shard threads may report errors concurrently
 std::string g_err;
 std::atomic<uint64_t> g_launches{0};
+thread_local bool t_capturing = false;  // stream capture records a launch, it does not perform one
 
 void set_err(const std::string& s) {
     std::lock_guard<std::mutex> lk(g_err_mu);
@@ -188,42 +189,57 @@ Device* current_device() {
 
 enum Op { OP_K1 = 0, OP_R1 = 1, OP_ED = 2 };
 
-int launch_op(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_msgs, const uint8_t* d_pks, size_t n,
-              uint8_t* d_out, uint8_t* d_status, cudaStream_t st) {
-    if (n == 0) return 0;
-    int max_g = op == OP_K1 ? d.grid_k1 : op == OP_R1 ? d.grid_r1 : d.grid_ed;
-    // Geometry: full 512-thread blocks (one per SM, all 16 warps phase-locked by the kernels' barriers) once the batch
-    // covers the device; smaller batches are spread over all SMs with proportionally smaller blocks instead of filling
-    // a few SMs to the brim (latency of the 64 ... 64k end of the batch-size sweep).
+// Launch geometry: full 512-thread blocks (one per SM, all 16 warps phase-locked by the kernels' barriers) once the batch
+// covers the device; smaller batches are spread over all SMs with proportionally smaller blocks instead of filling
+// a few SMs to the brim (latency of the 64 ... 64k end of the batch-size sweep).
+void launch_geometry(const Device& d, Op op, size_t n, int* grid, int* tpb_out) {
+    const int max_g = op == OP_K1 ? d.grid_k1 : op == OP_R1 ? d.grid_r1 : d.grid_ed;
     int tpb = kBlock;
     if (n < (size_t)d.sms * kBlock) {
         size_t per_sm = (n + d.sms - 1) / d.sms;
         tpb = (int)std::min<size_t>(kBlock, std::max<size_t>(32, (per_sm + 31) / 32 * 32));
     }
     size_t blocks = (n + tpb - 1) / tpb;
-    int grid = (int)std::min<size_t>(blocks, (size_t)max_g);
-    size_t chunks = op == OP_ED ? kEdBatchChunks : kSwBatchChunks;
-    if (ensure_scratch(d, chunks * (size_t)max_g * kBlock)) return 1;
+    *grid = (int)std::min<size_t>(blocks, (size_t)max_g);
+    *tpb_out = tpb;
+}
+
+// The kernels index their per-thread scratch by global thread id: `scratch` must hold chunks x grid x tpb Q4 and must not
+// be shared by two launches that may run concurrently.
+int launch_op_scratch(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_msgs, const uint8_t* d_pks, size_t n,
+                      uint8_t* d_out, uint8_t* d_status, Q4* scratch, cudaStream_t st) {
+    if (n == 0) return 0;
+    int grid, tpb;
+    launch_geometry(d, op, n, &grid, &tpb);
     // stage the fixed-base table in shared memory when the launch is big enough to amortise the copy (>= 1 full pass)
     const bool stage = d.smem_tables && n >= (size_t)d.sms * kBlock && tpb == kBlock;
     const u32 sw_words = stage ? (u32)kGTabEntries * 16 : 0, ed_words = stage ? (u32)kGTabEntries * 24 : 0;
     switch (op) {
         case OP_K1:
             ecrecover_kernel<CurveK1><<<grid, tpb, sw_words * 4, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, n, (Q4*)d_out,
-                                                                       d_status, d.scratch, d.k1g, sw_words);
+                                                                       d_status, scratch, d.k1g, sw_words);
             break;
         case OP_R1:
             ecrecover_kernel<CurveR1><<<grid, tpb, sw_words * 4, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, n, (Q4*)d_out,
-                                                                       d_status, d.scratch, d.r1g, sw_words);
+                                                                       d_status, scratch, d.r1g, sw_words);
             break;
         case OP_ED:
             ed25519_verify_kernel<<<grid, tpb, ed_words * 4, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, (const Q4*)d_pks, n,
-                                                                   d_out, d.scratch, d.edb, ed_words);
+                                                                   d_out, scratch, d.edb, ed_words);
             break;
     }
     CK(cudaGetLastError());
-    g_launches++;
+    if (!t_capturing) g_launches++;
     return 0;
+}
+
+int launch_op(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_msgs, const uint8_t* d_pks, size_t n,
+              uint8_t* d_out, uint8_t* d_status, cudaStream_t st) {
+    if (n == 0) return 0;
+    const int max_g = op == OP_K1 ? d.grid_k1 : op == OP_R1 ? d.grid_r1 : d.grid_ed;
+    const size_t chunks = op == OP_ED ? kEdBatchChunks : kSwBatchChunks;
+    if (ensure_scratch(d, chunks * (size_t)max_g * kBlock)) return 1;
+    return launch_op_scratch(d, op, d_sigs, d_msgs, d_pks, n, d_out, d_status, d.scratch, st);
 }
 
 // One shard on one device.  The shard is cut into up to kMaxChunks pieces that flow through a three-stage pipeline
@@ -455,6 +471,91 @@ void sw_bases(std::vector<uint32_t>& out, const u32* gxy_table_entry0, const u32
     }
 }
 
+
+// ---- streaming service mode -----------------------------------------------------------------------
+// A queue is a ring of `depth` slots on ONE device for ONE operation.  Every slot owns pinned host staging (inputs and
+// outputs), device buffers, its own per-thread scratch and its own stream, so the slots of a queue run concurrently on the
+// device: a request of a few thousand signatures occupies one or two warps per SM (launch_geometry), and up to 16 warps per
+// SM are resident, so `depth` small requests in flight multiply the throughput at the latency of one.  A slot's H2D copies,
+// kernel and D2H copies are replayed as one CUDA graph while the request size repeats (re-captured when it changes).
+// Replaces the per-call device creation / buffer allocation / blocking poll of src/gpu.rs:5-35,129-170.
+struct QSlot {
+    cudaStream_t st = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    uint8_t *h_in = nullptr, *h_out = nullptr;  // pinned: sigs (cap*64) | msgs (cap*32) | pks (cap*32); out (cap*64) | status (cap)
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    Q4* scratch = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    size_t exec_n = 0;
+    bool busy = false;
+    size_t n = 0;
+    float last_ms = 0;
+};
+
+}  // namespace
+
+struct sigops_queue {
+    std::mutex mu;
+    Device* dev = nullptr;
+    Op op = OP_K1;
+    size_t cap = 0;
+    bool graphs = true;
+    std::vector<QSlot> slots;
+    uint64_t graph_launches = 0, graph_captures = 0;
+};
+
+namespace {
+
+std::atomic<int> g_live_queues{0};
+
+inline size_t q_out_stride(Op op) { return op == OP_ED ? 1 : 64; }
+
+// enqueue one request of n signatures of slot s on stream st (also used under stream capture: no allocation, no sync)
+int queue_enqueue(sigops_queue* q, QSlot& s, size_t n, cudaStream_t st) {
+    const size_t cap = q->cap;
+    const Op op = q->op;
+    CK(cudaMemcpyAsync(s.d_in, s.h_in, n * 64, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.d_in + cap * 64, s.h_in + cap * 64, n * 32, cudaMemcpyHostToDevice, st));
+    if (op == OP_ED) CK(cudaMemcpyAsync(s.d_in + cap * 96, s.h_in + cap * 96, n * 32, cudaMemcpyHostToDevice, st));
+    uint8_t* d_status = op == OP_ED ? nullptr : s.d_out + cap * 64;
+    if (launch_op_scratch(*q->dev, op, s.d_in, s.d_in + cap * 64, s.d_in + cap * 96, n, s.d_out, d_status, s.scratch, st))
+        return 1;
+    CK(cudaMemcpyAsync(s.h_out, s.d_out, n * q_out_stride(op), cudaMemcpyDeviceToHost, st));
+    if (d_status) CK(cudaMemcpyAsync(s.h_out + cap * 64, d_status, n, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+void queue_free_slot(QSlot& s) {
+    if (s.exec) cudaGraphExecDestroy(s.exec);
+    if (s.st) cudaStreamDestroy(s.st);
+    if (s.t0) cudaEventDestroy(s.t0);
+    if (s.t1) cudaEventDestroy(s.t1);
+    if (s.h_in) cudaFreeHost(s.h_in);
+    if (s.h_out) cudaFreeHost(s.h_out);
+    if (s.d_in) cudaFree(s.d_in);
+    if (s.d_out) cudaFree(s.d_out);
+    if (s.scratch) cudaFree(s.scratch);
+    s = QSlot();
+}
+
+int queue_alloc_slot(sigops_queue* q, QSlot& s) {
+    const Device& d = *q->dev;
+    const size_t cap = q->cap;
+    const int max_g = q->op == OP_K1 ? d.grid_k1 : q->op == OP_R1 ? d.grid_r1 : d.grid_ed;
+    const size_t chunks = q->op == OP_ED ? kEdBatchChunks : kSwBatchChunks;
+    // launch_geometry never uses more than min(max_g * 512, n + 512) threads for n signatures
+    const size_t threads = std::min((size_t)max_g * kBlock, cap + (size_t)kBlock);
+    CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&s.t0));
+    CK(cudaEventCreate(&s.t1));
+    CK(cudaHostAlloc((void**)&s.h_in, cap * 128, cudaHostAllocPortable));
+    CK(cudaHostAlloc((void**)&s.h_out, cap * 65, cudaHostAllocPortable));
+    CK(cudaMalloc((void**)&s.d_in, cap * 128 + 64));
+    CK(cudaMalloc((void**)&s.d_out, cap * 65 + 64));
+    CK(cudaMalloc((void**)&s.scratch, chunks * threads * sizeof(Q4)));
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -466,6 +567,10 @@ int sigops_init(const int* device_ids, int n_devices) {
 
 int sigops_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
+    if (g_live_queues.load() > 0) {
+        set_err("sigops_shutdown: destroy every sigops_queue first");
+        return 1;
+    }
     for (auto& d : g_dev) {
         cudaSetDevice(d.id);
         if (d.d_in) cudaFree(d.d_in);
@@ -916,6 +1021,211 @@ int sigops_imad_peak(int kind, int iters, double* ops_per_sec, double* ms_out) {
     double ops = per_thread_iter * (double)iters * (double)grid * block;
     if (ops_per_sec) *ops_per_sec = ops / (ms * 1e-3);
     if (ms_out) *ms_out = ms;
+    return 0;
+}
+
+
+// ---- streaming service mode: C entry points ----------------------------------------------------------------------------
+int sigops_queue_create(int curve, int device_index, size_t max_batch, int depth, sigops_queue** out) {
+    if (!out) {
+        set_err("sigops_queue_create: out is NULL");
+        return 1;
+    }
+    *out = nullptr;
+    if (curve < SIGOPS_CURVE_SECP256K1 || curve > SIGOPS_CURVE_ED25519 || max_batch == 0 || max_batch > kMaxSubShard ||
+        depth < 1 || depth > SIGOPS_QUEUE_MAX_DEPTH) {
+        set_err("sigops_queue_create: bad arguments (curve 0..2, 1 <= max_batch <= 2^24, 1 <= depth <= 64)");
+        return 1;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (int rc = do_init(nullptr, 0)) return rc;
+    if (device_index < 0 || device_index >= (int)g_dev.size()) {
+        set_err("sigops_queue_create: device_index is not in the pool");
+        return 1;
+    }
+    sigops_queue* q = new sigops_queue();
+    q->dev = &g_dev[device_index];
+    q->op = (Op)curve;
+    q->cap = max_batch;
+    if (const char* e = getenv("SIGOPS_QUEUE_GRAPHS")) q->graphs = atoi(e) != 0;
+    q->slots.resize(depth);
+    if (cudaSetDevice(q->dev->id) != cudaSuccess) {
+        set_err("sigops_queue_create: cudaSetDevice failed");
+        delete q;
+        return 1;
+    }
+    for (auto& s : q->slots)
+        if (queue_alloc_slot(q, s)) {
+            for (auto& t : q->slots) queue_free_slot(t);
+            delete q;
+            return 1;
+        }
+    g_live_queues++;
+    *out = q;
+    return 0;
+}
+
+int sigops_queue_destroy(sigops_queue* q) {
+    if (!q) return 0;
+    {
+        std::lock_guard<std::mutex> lk(q->mu);
+        cudaSetDevice(q->dev->id);
+        for (auto& s : q->slots) {
+            if (s.st) cudaStreamSynchronize(s.st);
+            queue_free_slot(s);
+        }
+    }
+    delete q;
+    g_live_queues--;
+    return 0;
+}
+
+int sigops_queue_buffers(sigops_queue* q, int slot, uint8_t** sigs, uint8_t** msgs, uint8_t** pks, uint8_t** out,
+                         uint8_t** status) {
+    if (!q || slot < 0 || slot >= (int)q->slots.size()) {
+        set_err("sigops_queue_buffers: bad queue or slot");
+        return 1;
+    }
+    QSlot& s = q->slots[slot];
+    if (sigs) *sigs = s.h_in;
+    if (msgs) *msgs = s.h_in + q->cap * 64;
+    if (pks) *pks = q->op == OP_ED ? s.h_in + q->cap * 96 : nullptr;
+    if (out) *out = s.h_out;
+    if (status) *status = q->op == OP_ED ? nullptr : s.h_out + q->cap * 64;
+    return 0;
+}
+
+int sigops_queue_submit(sigops_queue* q, int slot, size_t n) {
+    if (!q || slot < 0 || slot >= (int)q->slots.size()) {
+        set_err("sigops_queue_submit: bad queue or slot");
+        return 1;
+    }
+    std::lock_guard<std::mutex> lk(q->mu);
+    QSlot& s = q->slots[slot];
+    if (s.busy) {
+        set_err("sigops_queue_submit: slot is in flight (wait for it first)");
+        return 1;
+    }
+    if (n > q->cap) {
+        set_err("sigops_queue_submit: n exceeds the queue's max_batch");
+        return 1;
+    }
+    s.n = n;
+    s.last_ms = 0;
+    if (n == 0) return 0;  // nothing to do: the slot stays free (src/secp256k1_ecdsa.rs:71-73)
+    CK(cudaSetDevice(q->dev->id));
+    if (q->graphs && s.exec_n != n) {
+        // (re)capture the slot's copy / kernel / copy sequence for this request size
+        cudaGraph_t g = nullptr;
+        CK(cudaStreamBeginCapture(s.st, cudaStreamCaptureModeThreadLocal));
+        t_capturing = true;
+        int rc = queue_enqueue(q, s, n, s.st);
+        t_capturing = false;
+        cudaError_t e = cudaStreamEndCapture(s.st, &g);
+        if (rc || e != cudaSuccess) {
+            if (g) cudaGraphDestroy(g);
+            if (!rc) set_err(std::string("cudaStreamEndCapture failed: ") + cudaGetErrorString(e));
+            return 1;
+        }
+        bool updated = false;
+        if (s.exec) {
+            cudaGraphExecUpdateResultInfo info;
+            updated = cudaGraphExecUpdate(s.exec, g, &info) == cudaSuccess;
+            if (!updated) {
+                cudaGetLastError();
+                cudaGraphExecDestroy(s.exec);
+                s.exec = nullptr;
+            }
+        }
+        if (!updated) {
+            e = cudaGraphInstantiate(&s.exec, g, 0);
+            if (e != cudaSuccess) {
+                cudaGraphDestroy(g);
+                s.exec = nullptr;
+                s.exec_n = 0;
+                set_err(std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(e));
+                return 1;
+            }
+        }
+        cudaGraphDestroy(g);
+        s.exec_n = n;
+        q->graph_captures++;
+    }
+    CK(cudaEventRecord(s.t0, s.st));
+    if (q->graphs) {
+        CK(cudaGraphLaunch(s.exec, s.st));
+        g_launches++;  // one fused kernel per request
+        q->graph_launches++;
+    } else if (queue_enqueue(q, s, n, s.st)) {
+        return 1;
+    }
+    CK(cudaEventRecord(s.t1, s.st));
+    s.busy = true;
+    return 0;
+}
+
+int sigops_queue_poll(sigops_queue* q, int slot, int* done) {
+    if (!q || slot < 0 || slot >= (int)q->slots.size() || !done) {
+        set_err("sigops_queue_poll: bad arguments");
+        return 1;
+    }
+    std::lock_guard<std::mutex> lk(q->mu);
+    QSlot& s = q->slots[slot];
+    if (!s.busy) {
+        *done = 1;
+        return 0;
+    }
+    cudaError_t e = cudaEventQuery(s.t1);
+    if (e == cudaErrorNotReady) {
+        *done = 0;
+        return 0;
+    }
+    if (e != cudaSuccess) {
+        set_err(std::string("sigops_queue_poll: ") + cudaGetErrorString(e));
+        return 1;
+    }
+    *done = 1;
+    return 0;
+}
+
+int sigops_queue_wait(sigops_queue* q, int slot, size_t* n_done, double* device_ms) {
+    if (!q || slot < 0 || slot >= (int)q->slots.size()) {
+        set_err("sigops_queue_wait: bad queue or slot");
+        return 1;
+    }
+    QSlot& s = q->slots[slot];
+    cudaEvent_t ev;
+    {
+        std::lock_guard<std::mutex> lk(q->mu);
+        if (!s.busy) {
+            if (n_done) *n_done = s.n;
+            if (device_ms) *device_ms = s.last_ms;
+            return 0;
+        }
+        ev = s.t1;
+    }
+    CK(cudaEventSynchronize(ev));  // outside the queue lock: other threads keep submitting to other slots
+    std::lock_guard<std::mutex> lk(q->mu);
+    CK(cudaEventElapsedTime(&s.last_ms, s.t0, s.t1));
+    s.busy = false;
+    if (n_done) *n_done = s.n;
+    if (device_ms) *device_ms = s.last_ms;
+    return 0;
+}
+
+int sigops_queue_info(sigops_queue* q, int* curve, int* device_index, size_t* max_batch, int* depth, uint64_t* graph_launches,
+                      uint64_t* graph_captures) {
+    if (!q) {
+        set_err("sigops_queue_info: queue is NULL");
+        return 1;
+    }
+    std::lock_guard<std::mutex> lk(q->mu);
+    if (curve) *curve = (int)q->op;
+    if (device_index) *device_index = (int)(q->dev - g_dev.data());
+    if (max_batch) *max_batch = q->cap;
+    if (depth) *depth = (int)q->slots.size();
+    if (graph_launches) *graph_launches = q->graph_launches;
+    if (graph_captures) *graph_captures = q->graph_captures;
     return 0;
 }
 
