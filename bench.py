@@ -32,6 +32,9 @@ import sys
 import threading
 import time
 
+# before anything creates the CUDA context: hardware work queues for the streaming-mode row (see sigops_init)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "oracle")):
     if p not in sys.path:
@@ -482,7 +485,7 @@ def run_sigops(args):
     #      sigops_queue, 1 / 4 / 16 in flight (pinned slot arrays, one CUDA graph per request) ----
     if rank == 0 and world == 1 and (args.curves == "all" or "secp256k1" in args.curves):
         pool = make_batch("secp256k1", 1 << 16, 1 << 16, 0x51600003, host_threads)
-        rows = [queue_throughput(w, "secp256k1", 1024, d, 64 * d if d > 1 else 100, pool) for d in (1, 4, 16)]
+        rows = [queue_throughput(w, "secp256k1", 1024, d, 64 * d if d > 1 else 100, pool) for d in (1, 4, 16, 32)]
         ext = ext or {}
         ext["secp256k1_queue_1024"] = {
             "rows": rows, "unit": "sigs/s",

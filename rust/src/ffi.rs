@@ -18,4 +18,18 @@ extern "C" {
     pub fn sigops_kernel_launches() -> u64;
     pub fn sigops_host_alloc(bytes: usize) -> *mut c_void;
     pub fn sigops_host_free(p: *mut c_void);
+    // streaming service mode (include/sigops.h, "Streaming service mode")
+    pub fn sigops_queue_create(curve: c_int, device_index: c_int, max_batch: usize, depth: c_int, out: *mut *mut SigopsQueue) -> c_int;
+    pub fn sigops_queue_destroy(q: *mut SigopsQueue) -> c_int;
+    pub fn sigops_queue_buffers(q: *mut SigopsQueue, slot: c_int, sigs: *mut *mut u8, msgs: *mut *mut u8, pks: *mut *mut u8, out: *mut *mut u8, status: *mut *mut u8) -> c_int;
+    pub fn sigops_queue_submit(q: *mut SigopsQueue, slot: c_int, n: usize) -> c_int;
+    pub fn sigops_queue_poll(q: *mut SigopsQueue, slot: c_int, done: *mut c_int) -> c_int;
+    pub fn sigops_queue_wait(q: *mut SigopsQueue, slot: c_int, n_done: *mut usize, device_ms: *mut f64) -> c_int;
+    pub fn sigops_queue_info(q: *mut SigopsQueue, curve: *mut c_int, device_index: *mut c_int, max_batch: *mut usize, depth: *mut c_int, graph_launches: *mut u64, graph_captures: *mut u64) -> c_int;
+}
+
+/// Opaque `sigops_queue` of the C ABI.
+#[repr(C)]
+pub struct SigopsQueue {
+    _private: [u8; 0],
 }

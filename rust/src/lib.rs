@@ -8,6 +8,7 @@ pub mod ffi;
 pub mod precompute;
 pub mod secp256k1_ecdsa;
 pub mod secp256r1_ecdsa;
+pub mod service;
 
 /// This error is raised if the device path fails to execute (reference: "if the shader silently fails to execute",
 /// src/lib.rs:12-14).  Here: any nonzero return code of libsigops (no CUDA device, CUDA runtime error).

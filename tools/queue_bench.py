@@ -49,7 +49,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--curves", default="secp256k1,secp256r1,ed25519")
     ap.add_argument("--sizes", default="256,1024,4096,16384")
-    ap.add_argument("--depths", default="1,2,4,8,16")
+    ap.add_argument("--depths", default="1,2,4,8,16,32")
     ap.add_argument("--requests-per-slot", type=int, default=40)
     args = ap.parse_args()
     lib = w.load()
@@ -58,7 +58,8 @@ def main():
     threads = coracle.host_threads()
     res = {"config": "requests through service.SigQueue on one GPU: host submit -> wait per request, H2D + fused kernel + D2H "
                      "inside; `blocking` = the same requests through the blocking C entry point, one at a time",
-           "graphs": os.environ.get("SIGOPS_QUEUE_GRAPHS", "1") != "0", "curves": {}}
+           "graphs": os.environ.get("SIGOPS_QUEUE_GRAPHS", "1") != "0",
+           "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), "curves": {}}
     for curve in args.curves.split(","):
         pool = bench.make_batch(curve, 1 << 16, 1 << 16, 0x51600003, threads)
         rows = []

@@ -39,6 +39,9 @@ def load() -> ctypes.CDLL:
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). There is no CPU fallback."
         )
+    # many small requests in flight (service.SigQueue) need more than the default 8 hardware work queues; must be set
+    # before the process creates its CUDA context (the library sets the same default in sigops_init)
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     lib = ctypes.CDLL(LIB_PATH)
     c = ctypes
     vp, sz, i32, u32p = c.c_void_p, c.c_size_t, c.c_int, c.POINTER(c.c_uint32)

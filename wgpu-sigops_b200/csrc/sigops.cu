@@ -144,6 +144,10 @@ int init_device(Device& d, int id) {
 
 int do_init(const int* ids, int n) {
     if (g_inited) return 0;
+    // The streaming mode keeps many small launches in flight on separate streams; with the default of 8 hardware work
+    // queues no more than ~4 requests overlap and further submits block in the driver (measured: profiles/r01_queue_sweep.json).
+    // Only effective if this process has not created its CUDA context yet; an explicit setting wins.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
