@@ -377,7 +377,7 @@ SG_HD void merge_even_odd(u32* r, const u32* e, const u32* o) {
 // the NEXT row's top product a7*b_(j+1) -- which lands on the fresh pair just above -- as a fifth element, and that next
 // row then runs three products plus a two-limb carry propagation (mad_row5 / mad_row3c): no carry limb is ever
 // materialised except the final o[14].
-SG_HD void mul8x8(u32* r, const u32* a, const u32* b) {
+SG_HD void mul8x8_school(u32* r, const u32* a, const u32* b) {
     u32 e[16], o[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) {
@@ -423,6 +423,175 @@ SG_HD void mul8x8(u32* r, const u32* a, const u32* b) {
     }
 #endif
     merge_even_odd(r, e, o);
+}
+
+// ---- one-level Karatsuba variant (experiment, -DSG_KARATSUBA): three 4x4 products (48 wide MACs instead of 64) and
+// ~65 more add / logic instructions.  Trades multiplier-pipe time for ALU-pipe time; see profiles/r01_variants.md.
+// r[0..8) = a[0..4) * b[0..4): 16 wide MACs on even/odd column accumulators, carries in explicit limbs
+SG_HD void mul4x4(u32* r, const u32* a, const u32* b) {
+    u32 e[8], o[8];
+    mul_wide(e + 0, a[0], b[0]);
+    mul_wide(e + 2, a[2], b[0]);
+    mul_wide(o + 0, a[1], b[0]);
+    mul_wide(o + 2, a[3], b[0]);
+    e[4] = e[5] = e[6] = e[7] = 0;
+    o[4] = o[5] = o[6] = o[7] = 0;
+    o[4] = mad_row2(o + 0, a[0], a[2], b[1]);
+    mad_row2(e + 2, a[1], a[3], b[1]);
+    e[6] = mad_row2(e + 2, a[0], a[2], b[2]);
+    mad_row2(o + 2, a[1], a[3], b[2]);
+    o[6] = mad_row2(o + 2, a[0], a[2], b[3]);
+    mad_row2(e + 4, a[1], a[3], b[3]);
+    r[0] = e[0];
+#if SG_PTX
+    asm("add.cc.u32 %0, %7, %14;\n\t"
+        "addc.cc.u32 %1, %8, %15;\n\t"
+        "addc.cc.u32 %2, %9, %16;\n\t"
+        "addc.cc.u32 %3, %10, %17;\n\t"
+        "addc.cc.u32 %4, %11, %18;\n\t"
+        "addc.cc.u32 %5, %12, %19;\n\t"
+        "addc.u32 %6, %13, %20;"
+        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(o[0]), "r"(o[1]), "r"(o[2]),
+          "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]));
+#else
+    u64 t = 0;
+    for (int k = 1; k < 8; k++) {
+        t += (u64)e[k] + o[k - 1];
+        r[k] = (u32)t;
+        t >>= 32;
+    }
+#endif
+}
+
+// s[0..4) = x[0..4) + x[4..8), returns the carry (0 or 1)
+SG_HD u32 fold_halves(u32* s, const u32* x) {
+    u32 c;
+#if SG_PTX
+    asm("add.cc.u32 %0, %5, %9;\n\t"
+        "addc.cc.u32 %1, %6, %10;\n\t"
+        "addc.cc.u32 %2, %7, %11;\n\t"
+        "addc.cc.u32 %3, %8, %12;\n\t"
+        "addc.u32 %4, 0, 0;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(c)
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]));
+#else
+    u64 t = 0;
+    for (int i = 0; i < 4; i++) {
+        t += (u64)x[i] + x[i + 4];
+        s[i] = (u32)t;
+        t >>= 32;
+    }
+    c = (u32)t;
+#endif
+    return c;
+}
+
+SG_HD void mul8x8_kara(u32* r, const u32* a, const u32* b) {
+    u32 z0[8], z2[8], zm[9], sa[4], sb[4];
+    mul4x4(z0, a, b);
+    mul4x4(z2, a + 4, b + 4);
+    const u32 ca = fold_halves(sa, a), cb = fold_halves(sb, b);
+    mul4x4(zm, sa, sb);
+    // (sa + ca 2^128)(sb + cb 2^128) = zm + (ca ? sb : 0) 2^128 + (cb ? sa : 0) 2^128 + (ca & cb) 2^256
+    const u32 ma = 0u - ca, mb = 0u - cb;
+    u32 ta[4], tb[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        ta[i] = sb[i] & ma;
+        tb[i] = sa[i] & mb;
+    }
+    zm[8] = ca & cb;
+#if SG_PTX
+    asm("add.cc.u32 %0, %0, %5;\n\t"
+        "addc.cc.u32 %1, %1, %6;\n\t"
+        "addc.cc.u32 %2, %2, %7;\n\t"
+        "addc.cc.u32 %3, %3, %8;\n\t"
+        "addc.u32 %4, %4, 0;\n\t"
+        "add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, %10;\n\t"
+        "addc.cc.u32 %2, %2, %11;\n\t"
+        "addc.cc.u32 %3, %3, %12;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(zm[4]), "+r"(zm[5]), "+r"(zm[6]), "+r"(zm[7]), "+r"(zm[8])
+        : "r"(ta[0]), "r"(ta[1]), "r"(ta[2]), "r"(ta[3]), "r"(tb[0]), "r"(tb[1]), "r"(tb[2]), "r"(tb[3]));
+    // zm -= z0; zm -= z2   (the middle term a_lo b_hi + a_hi b_lo, below 2^257)
+    asm("sub.cc.u32 %0, %0, %9;\n\t"
+        "subc.cc.u32 %1, %1, %10;\n\t"
+        "subc.cc.u32 %2, %2, %11;\n\t"
+        "subc.cc.u32 %3, %3, %12;\n\t"
+        "subc.cc.u32 %4, %4, %13;\n\t"
+        "subc.cc.u32 %5, %5, %14;\n\t"
+        "subc.cc.u32 %6, %6, %15;\n\t"
+        "subc.cc.u32 %7, %7, %16;\n\t"
+        "subc.u32 %8, %8, 0;\n\t"
+        "sub.cc.u32 %0, %0, %17;\n\t"
+        "subc.cc.u32 %1, %1, %18;\n\t"
+        "subc.cc.u32 %2, %2, %19;\n\t"
+        "subc.cc.u32 %3, %3, %20;\n\t"
+        "subc.cc.u32 %4, %4, %21;\n\t"
+        "subc.cc.u32 %5, %5, %22;\n\t"
+        "subc.cc.u32 %6, %6, %23;\n\t"
+        "subc.cc.u32 %7, %7, %24;\n\t"
+        "subc.u32 %8, %8, 0;"
+        : "+r"(zm[0]), "+r"(zm[1]), "+r"(zm[2]), "+r"(zm[3]), "+r"(zm[4]), "+r"(zm[5]), "+r"(zm[6]), "+r"(zm[7]), "+r"(zm[8])
+        : "r"(z0[0]), "r"(z0[1]), "r"(z0[2]), "r"(z0[3]), "r"(z0[4]), "r"(z0[5]), "r"(z0[6]), "r"(z0[7]), "r"(z2[0]),
+          "r"(z2[1]), "r"(z2[2]), "r"(z2[3]), "r"(z2[4]), "r"(z2[5]), "r"(z2[6]), "r"(z2[7]));
+    // r = z0 + zm 2^128 + z2 2^256
+    r[0] = z0[0];
+    r[1] = z0[1];
+    r[2] = z0[2];
+    r[3] = z0[3];
+    asm("add.cc.u32 %0, %12, %20;\n\t"
+        "addc.cc.u32 %1, %13, %21;\n\t"
+        "addc.cc.u32 %2, %14, %22;\n\t"
+        "addc.cc.u32 %3, %15, %23;\n\t"
+        "addc.cc.u32 %4, %16, %24;\n\t"
+        "addc.cc.u32 %5, %17, %25;\n\t"
+        "addc.cc.u32 %6, %18, %26;\n\t"
+        "addc.cc.u32 %7, %19, %27;\n\t"
+        "addc.cc.u32 %8, %29, %28;\n\t"
+        "addc.cc.u32 %9, %30, 0;\n\t"
+        "addc.cc.u32 %10, %31, 0;\n\t"
+        "addc.u32 %11, %32, 0;"
+        : "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
+          "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(z0[4]), "r"(z0[5]), "r"(z0[6]), "r"(z0[7]), "r"(z2[0]), "r"(z2[1]), "r"(z2[2]), "r"(z2[3]), "r"(zm[0]),
+          "r"(zm[1]), "r"(zm[2]), "r"(zm[3]), "r"(zm[4]), "r"(zm[5]), "r"(zm[6]), "r"(zm[7]), "r"(zm[8]), "r"(z2[4]),
+          "r"(z2[5]), "r"(z2[6]), "r"(z2[7]));
+#else
+    u64 t = 0;
+    for (int i = 0; i < 4; i++) {
+        t += (u64)zm[4 + i] + ta[i] + tb[i];
+        zm[4 + i] = (u32)t;
+        t >>= 32;
+    }
+    zm[8] += (u32)t;
+    for (int pass = 0; pass < 2; pass++) {
+        const u32* z = pass ? z2 : z0;
+        u64 bw = 0;
+        for (int i = 0; i < 9; i++) {
+            u64 d = (u64)zm[i] - (i < 8 ? z[i] : 0u) - bw;
+            zm[i] = (u32)d;
+            bw = (d >> 32) & 1;
+        }
+    }
+    for (int i = 0; i < 4; i++) r[i] = z0[i];
+    t = 0;
+    for (int i = 4; i < 16; i++) {
+        t += (u64)(i < 8 ? z0[i] : z2[i - 8]) + (i < 13 ? zm[i - 4] : 0);
+        r[i] = (u32)t;
+        t >>= 32;
+    }
+#endif
+}
+
+SG_HD void mul8x8(u32* r, const u32* a, const u32* b) {
+#if defined(SG_KARATSUBA)
+    mul8x8_kara(r, a, b);
+#else
+    mul8x8_school(r, a, b);
+#endif
 }
 
 // r[0..16) += sum a_i^2 * 2^(64 i)
