@@ -161,3 +161,26 @@ def test_queue_driven_by_several_threads(sigops):
         for t in ts:
             t.join()
     assert not errors, errors
+
+
+@pytest.mark.gpu
+def test_queues_on_two_devices(sigops):
+    """One queue per device of the pool, driven alternately: independent shards, no exchange between devices."""
+    lib = sigops.load()
+    if lib.sigops_num_devices() < 2:
+        pytest.skip("one visible GPU")
+    sizes = [200] * 8
+    reqs, exp = _requests("secp256r1", sizes, seed=0x51600103)
+    with sigops.service.SigQueue("secp256r1", 200, depth=2, device_index=0) as q0, \
+            sigops.service.SigQueue("secp256r1", 200, depth=2, device_index=1) as q1:
+        assert q0.info()["device_index"] == 0 and q1.info()["device_index"] == 1
+        qs = (q0, q1)
+        for i, (sg, m) in enumerate(reqs):
+            q, slot = qs[i % 2], (i // 2) % 2
+            q.wait(slot)
+            q.sigs(slot)[:200], q.msgs(slot)[:200] = sg, m
+            q.submit(slot, 200)
+            out, st = q.wait(slot)
+            _check("secp256r1", (out, st), exp[i])
+    with pytest.raises(sigops.ShaderFailureError):
+        sigops.service.SigQueue("secp256k1", 64, 1, device_index=lib.sigops_num_devices())
