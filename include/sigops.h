@@ -211,7 +211,11 @@ enum {
     SIGOPS_UNIT_R1_INV_FERMAT = 34,
     SIGOPS_UNIT_ED_INV_FERMAT = 35,
     SIGOPS_UNIT_SHA256_64 = 36,      /* in 16 (64 bytes)        out 8  : SHA-256 digest bytes           */
-    SIGOPS_UNIT_COUNT = 37
+    /* raw-representation probes of the base fields (field id 0 = secp256k1, 1 = P-256, 2 = 2^255-19 in word 0): the operands
+     * are the INTERNAL, weakly reduced limbs (any value below 2^256), so that the once-in-2^31 fix-up paths can be hit */
+    SIGOPS_UNIT_RAW_ADDSUB = 37,     /* in 17 (id, a, b)        out 16 : a+b, a-b as internal limbs     */
+    SIGOPS_UNIT_RAW_REDUCE16 = 38,   /* in 17 (id, t[16])       out 8  : reduce16(t), ids 0 and 2 only  */
+    SIGOPS_UNIT_COUNT = 39
 };
 
 #ifdef __cplusplus

@@ -20,6 +20,10 @@ def test_field_r1(gpu_units):
     uc.check_field(gpu_units, "R1", o.R1.p, True, nrand=20000)
 
 
+def test_raw_fixup_paths(gpu_units):
+    uc.check_raw_fixups(gpu_units, nrand=4000)
+
+
 def test_wide_products(gpu_units):
     uc.check_wide(gpu_units, nrand=20000)
 

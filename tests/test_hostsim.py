@@ -19,6 +19,10 @@ def test_field_r1(sim_units):
     uc.check_field(sim_units, "R1", o.R1.p, True)
 
 
+def test_raw_fixup_paths(sim_units):
+    uc.check_raw_fixups(sim_units)
+
+
 def test_wide_products(sim_units):
     uc.check_wide(sim_units)
 

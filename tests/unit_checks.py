@@ -31,6 +31,75 @@ def check_field(U, prefix, p, weak, nrand=1500, seed=1):
         assert from_words(w) == a * a % p, (prefix, "SQR", hex(a))
 
 
+def check_raw_fixups(U, nrand=400, seed=11):
+    """The once-in-2^31 fix-up paths of the weakly reduced fields (cold functions in field.cuh): additions whose folded carry
+    leaves the low limbs or wraps past 2^256 a second time, the mirror-image subtractions, and products whose second fold
+    carries.  Operands are internal limbs (any value below 2^256) through the RAW_* unit ops."""
+    rng = random.Random(seed)
+    M = 1 << 256
+    fields = ((0, o.K1.p, (1 << 32) + 977, 64), (1, o.R1.p, M - o.R1.p, 256), (2, o.ED_P, 38, 32))
+    rows, meta = [], []
+    for fid, p, c, low_bits in fields:
+        low = 1 << low_bits
+        xs = [M - 2, M - c, M - c - 1, M - c + 1, p, p - 1, p + 1 if p + 1 < M - 1 else p, low - 1, low - c, low - c - 1, low - c + 1,
+              0, 1, c, c - 1]
+        ys = [1, 2, c - 1, c, c + 1, low - 1, low, low + 1, 5 * low + (c - 1), 5 * low + c, M - 1, p, p - 1]
+        for _ in range(nrand):
+            hi = rng.getrandbits(256 - low_bits) if low_bits < 256 else 0
+            xs.append(((hi << low_bits) | (low - 1 - rng.randrange(2 * c if c < low else 1000))) % (M - 1))
+            xs.append(M - 1 - rng.randrange(1, 4 * c if c < (1 << 40) else 1 << 40))
+            ys.append((hi << low_bits) | rng.randrange(2 * c if c < low else 1000))
+            ys.append(rng.randrange(1, 4 * c if c < (1 << 40) else 1 << 40))
+        for x in xs:  # a + b = 2^256 + x
+            x %= M - 1
+            a = rng.randrange(x + 1, M)
+            b = M + x - a
+            rows.append([fid] + _w(a) + _w(b))
+            meta.append((p, a, b))
+        for y in ys:  # a - b = y - 2^256
+            y = max(1, y % M)
+            a = rng.randrange(0, y)
+            b = a + M - y
+            rows.append([fid] + _w(a) + _w(b))
+            meta.append((p, a, b))
+    out = U.run_words("RAW_ADDSUB", np.array(rows, dtype=np.uint32))
+    for (p, a, b), w in zip(meta, out):
+        s, d = from_words(w[:8]), from_words(w[8:])
+        assert s % p == (a + b) % p, ("add", hex(a), hex(b))
+        assert d % p == (a - b) % p, ("sub", hex(a), hex(b))
+    # products: reduce16 of crafted 512-bit values for the two special primes
+    rows, meta, cold = [], [], 0
+    for fid, p, c, top_limbs in ((0, o.K1.p, (1 << 32) + 977, 3), (2, o.ED_P, 38, 2)):
+        lowm = 1 << (32 * top_limbs)
+        for i in range(4 * nrand):
+            t_hi = rng.getrandbits(256) if i % 3 else M - 1 - rng.getrandbits(20)
+            s1 = t_hi * c
+            kind = i % 4
+            if kind == 0:    # low limbs of the first fold's result all ones: the second fold's carry leaves them
+                target = (rng.getrandbits(256) | (lowm - 1)) - rng.randrange(8)
+            elif kind == 1:  # ... and every limb above them all ones too: second wrap past 2^256
+                target = M - 1 - rng.randrange(1 << 12)
+            elif kind == 2:
+                target = rng.getrandbits(256)
+            else:
+                target = (rng.getrandbits(256) | (lowm - 1)) - rng.randrange(c * 40)
+            t_lo = (target - s1) % M
+            t = (t_hi << 256) | t_lo
+            acc = t_lo + s1
+            f = (acc >> 256) * c
+            cold += ((acc % lowm) + f >= lowm)
+            rows.append([fid] + _w(t, 16))
+            meta.append((p, t))
+    assert cold > nrand  # the crafted cases really reach the cold path
+    out = U.run_words("RAW_REDUCE16", np.array(rows, dtype=np.uint32))
+    for (p, t), w in zip(meta, out):
+        assert from_words(w) % p == t % p, hex(t)
+
+
+def _w(x, n=8):
+    return [(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)]
+
+
 def check_wide(U, nrand=1500, seed=2):
     rng = random.Random(seed)
     pairs = [(rand256(rng), rand256(rng)) for _ in range(nrand)] + [(2**256 - 1, 2**256 - 1), (0, 0), (2**256 - 1, 1)]

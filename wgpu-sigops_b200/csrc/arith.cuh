@@ -163,6 +163,146 @@ SG_HD u32 sub8_small(u32* r, u32 lo, u32 hi) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Short carry chains for the modular fix-ups.  A fix-up adds (or subtracts) a one- or two-limb constant; its carry leaves
+// the low limbs about once in 2^31 operations, so the hot path stops there and hands the pending carry to a COLD
+// block that ptxas cannot if-convert (SG_RARE / SG_COLD below).  (Written as `if (carry) add8_small(...)` the once-in-2^31 path
+// became 8 predicated instructions issued by every field operation: 13 % of a secp256k1 recovery's issue slots.)
+// ---------------------------------------------------------------------------------------
+// Two forms, chosen per field by measurement (profiles/r01_variants.md):
+//   CALL: the cold path is a __noinline__ function -- smallest code, but every call site carries the ABI's register
+//         constraints (more spills in the P-256 kernel: -2.6 %);
+//   LOOP: the cold path is inlined behind a loop whose trip count (0 or 1) the compiler cannot see -- a backward branch
+//         is never if-converted and there is no call, but the code grows (ed25519: -4 % against CALL) and cicc takes longer.
+#if !defined(__CUDACC__)
+#define SG_COLD_CALL inline
+#define SG_COLD_LOOP inline
+#define SG_RARE_CALL(c) if (c)
+#define SG_RARE_LOOP(c) if (c)
+#else
+#define SG_COLD_CALL __host__ __device__ __noinline__
+#define SG_COLD_LOOP __host__ __device__ __forceinline__
+#define SG_RARE_CALL(c) if (c)
+#define SG_RARE_LOOP(c) for (u32 sg_rare_ = (c); sg_rare_ != 0u; --sg_rare_)
+#endif
+#if defined(SG_K1_LOOP)
+#define SG_COLD_K1 SG_COLD_LOOP
+#define SG_RARE_K1 SG_RARE_LOOP
+#else
+#define SG_COLD_K1 SG_COLD_CALL
+#define SG_RARE_K1 SG_RARE_CALL
+#endif
+#if defined(SG_ED_LOOP)
+#define SG_COLD_ED SG_COLD_LOOP
+#define SG_RARE_ED SG_RARE_LOOP
+#else
+#define SG_COLD_ED SG_COLD_CALL
+#define SG_RARE_ED SG_RARE_CALL
+#endif
+#if defined(SG_R1_CALL)
+#define SG_COLD_R1 SG_COLD_CALL
+#define SG_RARE_R1 SG_RARE_CALL
+#else
+#define SG_COLD_R1 SG_COLD_LOOP
+#define SG_RARE_R1 SG_RARE_LOOP
+#endif
+
+// r[0] += v; returns the carry out of limb 0
+SG_HD u32 add1_c(u32* r, u32 v) {
+    u32 c;
+#if SG_PTX
+    asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, 0, 0;" : "+r"(r[0]), "=r"(c) : "r"(v));
+#else
+    u64 t = (u64)r[0] + v;
+    r[0] = (u32)t;
+    c = (u32)(t >> 32);
+#endif
+    return c;
+}
+SG_HD u32 sub1_b(u32* r, u32 v) {
+    u32 c;
+#if SG_PTX
+    asm("sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, 0, 0;" : "+r"(r[0]), "=r"(c) : "r"(v));
+    c &= 1u;
+#else
+    u64 t = (u64)r[0] - v;
+    r[0] = (u32)t;
+    c = (u32)(t >> 32) & 1u;
+#endif
+    return c;
+}
+// r[0..2) += (lo, hi); returns the carry out of limb 1
+SG_HD u32 add2_c(u32* r, u32 lo, u32 hi) {
+    u32 c;
+#if SG_PTX
+    asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, 0, 0;"
+        : "+r"(r[0]), "+r"(r[1]), "=r"(c)
+        : "r"(lo), "r"(hi));
+#else
+    u64 t = (u64)r[0] + lo;
+    r[0] = (u32)t;
+    t = (t >> 32) + r[1] + hi;
+    r[1] = (u32)t;
+    c = (u32)(t >> 32);
+#endif
+    return c;
+}
+SG_HD u32 sub2_b(u32* r, u32 lo, u32 hi) {
+    u32 c;
+#if SG_PTX
+    asm("sub.cc.u32 %0, %0, %3;\n\tsubc.cc.u32 %1, %1, %4;\n\tsubc.u32 %2, 0, 0;"
+        : "+r"(r[0]), "+r"(r[1]), "=r"(c)
+        : "r"(lo), "r"(hi));
+    c &= 1u;
+#else
+    u64 t = (u64)r[0] - lo;
+    r[0] = (u32)t;
+    u64 bw = (t >> 32) & 1;
+    t = (u64)r[1] - hi - bw;
+    r[1] = (u32)t;
+    c = (u32)(t >> 32) & 1u;
+#endif
+    return c;
+}
+// r[0..3) += (l0, l1, l2); returns the carry out of limb 2
+SG_HD u32 add3_c(u32* r, u32 l0, u32 l1, u32 l2) {
+    u32 c;
+#if SG_PTX
+    asm("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %5;\n\taddc.cc.u32 %2, %2, %6;\n\taddc.u32 %3, 0, 0;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "=r"(c)
+        : "r"(l0), "r"(l1), "r"(l2));
+#else
+    u64 t = (u64)r[0] + l0;
+    r[0] = (u32)t;
+    t = (t >> 32) + r[1] + l1;
+    r[1] = (u32)t;
+    t = (t >> 32) + r[2] + l2;
+    r[2] = (u32)t;
+    c = (u32)(t >> 32);
+#endif
+    return c;
+}
+// cold helpers: r[K..8) += 1 / -= 1, returns the carry / borrow out of limb 7
+template <int K>
+SG_HD u32 inc_from(u32* r) {
+    u32 c = 1;
+    for (int i = K; i < 8; i++) {
+        r[i] += c;
+        c = c & (u32)(r[i] == 0);
+    }
+    return c;
+}
+template <int K>
+SG_HD u32 dec_from(u32* r) {
+    u32 b = 1;
+    for (int i = K; i < 8; i++) {
+        const u32 was = r[i];
+        r[i] -= b;
+        b = b & (u32)(was == 0);
+    }
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------
 // wide multiply-accumulate rows.  acc[0..2n) += {x0,..,x(n-1)} * b, the n wide products landing on the
 // aligned limb pairs (0,1),(2,3),...; one carry chain; returns the carry out of the top limb.
 // ---------------------------------------------------------------------------------------

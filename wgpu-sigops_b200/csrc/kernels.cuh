@@ -307,9 +307,28 @@ SG_HD void unit_shape(int op, int& in_w, int& out_w) {
             in_w = 32;
             out_w = 17;
             break;
+        case SIGOPS_UNIT_RAW_ADDSUB:
+            in_w = 17;
+            out_w = 16;
+            break;
+        case SIGOPS_UNIT_RAW_REDUCE16:
+            in_w = 17;
+            out_w = 8;
+            break;
         default:
             break;
     }
+}
+
+template <class F>
+SG_HD void unit_raw_addsub(u32* out, const u32* in) {
+    Fe a, b, s, d;
+    copy8(a.v, in);
+    copy8(b.v, in + 8);
+    F::add(s, a, b);
+    F::sub(d, a, b);
+    copy8(out, s.v);
+    copy8(out + 8, d.v);
 }
 
 template <class F>
@@ -452,6 +471,15 @@ SG_HD void unit_dispatch(int op, u32* out, const u32* in, const TabRef& tab, con
             out[11] = s.neg2;
             break;
         }
+        case SIGOPS_UNIT_RAW_ADDSUB:
+            if (in[0] == 0) unit_raw_addsub<FpK1>(out, in + 1);
+            else if (in[0] == 1) unit_raw_addsub<FpR1>(out, in + 1);
+            else unit_raw_addsub<Fp25519>(out, in + 1);
+            break;
+        case SIGOPS_UNIT_RAW_REDUCE16:
+            if (in[0] == 0) FpK1::reduce16(out, in + 1);
+            else Fp25519::reduce16(out, in + 1);
+            break;
         case SIGOPS_UNIT_MUL8X8:
             mul8x8(out, in, in + 8);
             break;
