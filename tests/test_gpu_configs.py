@@ -76,6 +76,28 @@ def test_config5_mixed_sweep(sigops, n):
     assert (sigops.ed25519_eddsa.ecverify_array(s, m, pk) == v).all()
 
 
+@pytest.mark.parametrize("n", [75776 + 1, 75776 + 40000, 2 * 75776 + 56832, 3 * 75776 + 5])
+def test_tail_launch_boundaries(sigops, n):
+    """Shards of w.f waves (one wave = 148 SMs x 512 threads on a B200) with f <= 3/4 run as a main launch of whole waves
+    plus a separate, smaller launch for the tail: rows on both sides of the seam, edge rows included, must be exact, and the
+    result must not depend on the split (SIGOPS_TAIL_SPLIT=0 is the single-launch path)."""
+    import os
+
+    s, m, pk, st, _ = batches.ecdsa_batch(0, n, edge_every=101, seed=21)
+    out, got = sigops.secp256k1_ecdsa.ecrecover_with_status(s, m)
+    assert (out == pk).all() and (got == st).all()
+    s2, m2, pk2, v2, _ = batches.ed25519_batch(n, edge_every=7, seed=22)
+    got_v = sigops.ed25519_eddsa.ecverify_array(s2, m2, pk2)
+    assert (got_v == v2).all()
+    os.environ["SIGOPS_TAIL_SPLIT"] = "0"
+    try:
+        out0, got0 = sigops.secp256k1_ecdsa.ecrecover_with_status(s, m)
+        v0 = sigops.ed25519_eddsa.ecverify_array(s2, m2, pk2)
+    finally:
+        del os.environ["SIGOPS_TAIL_SPLIT"]
+    assert (out0 == out).all() and (got0 == got).all() and (v0 == got_v).all()
+
+
 def test_multi_device_sharding_matches_single(sigops):
     """When the box has more than one GPU the host entry point shards the batch; the result must not depend on it."""
     lib = sigops.load()

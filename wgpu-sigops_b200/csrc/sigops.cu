@@ -210,9 +210,32 @@ void launch_geometry(const Device& d, Op op, size_t n, int* grid, int* tpb_out) 
 
 // The kernels index their per-thread scratch by global thread id: `scratch` must hold chunks x grid x tpb Q4 and must not
 // be shared by two launches that may run concurrently.
+// A launch of w.f waves (one wave = SMs x 512 signatures, one per thread) costs ceil(w.f) full passes of ~1.65 ms: the last,
+// partial pass runs every thread (rows past the end are clamped) at 16 warps per SM.  When the tail is at most
+// kTailSplitNum/kTailSplitDen of a wave it is launched on its own right behind the main part, with the small-batch
+// geometry: fewer warps per SM finish a pass sooner (0.85 ms at one warp per scheduler).  Matters for shards of one to a
+// few waves -- the 1M block cut over 4 or 8 GPUs, the middle of the batch-size sweep.
+constexpr size_t kTailSplitNum = 3, kTailSplitDen = 4;
+size_t tail_split(const Device& d, size_t n) {  // signatures in the main launch (n if no split)
+    const size_t wave = (size_t)d.sms * kBlock;
+    if (n < wave) return n;
+    const size_t tail = n % wave;
+    if (tail == 0 || tail * kTailSplitDen > wave * kTailSplitNum) return n;
+    if (const char* e = getenv("SIGOPS_TAIL_SPLIT"))
+        if (atoi(e) == 0) return n;
+    return n - tail;
+}
+
 int launch_op_scratch(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_msgs, const uint8_t* d_pks, size_t n,
                       uint8_t* d_out, uint8_t* d_status, Q4* scratch, cudaStream_t st) {
     if (n == 0) return 0;
+    const size_t main_n = tail_split(d, n);
+    if (main_n < n) {
+        const size_t os = op == OP_ED ? 1 : 64;
+        if (launch_op_scratch(d, op, d_sigs, d_msgs, d_pks, main_n, d_out, d_status, scratch, st)) return 1;
+        return launch_op_scratch(d, op, d_sigs + main_n * 64, d_msgs + main_n * 32, d_pks ? d_pks + main_n * 32 : nullptr,
+                                 n - main_n, d_out + main_n * os, d_status ? d_status + main_n : nullptr, scratch, st);
+    }
     int grid, tpb;
     launch_geometry(d, op, n, &grid, &tpb);
     // stage the fixed-base table in shared memory when the launch is big enough to amortise the copy (>= 1 full pass)
@@ -1158,7 +1181,7 @@ int sigops_queue_submit(sigops_queue* q, int slot, size_t n) {
     CK(cudaEventRecord(s.t0, s.st));
     if (q->graphs) {
         CK(cudaGraphLaunch(s.exec, s.st));
-        g_launches++;  // one fused kernel per request
+        g_launches += tail_split(*q->dev, n) < n ? 2 : 1;  // the fused kernel (twice when the tail is launched on its own)
         q->graph_launches++;
     } else if (queue_enqueue(q, s, n, s.st)) {
         return 1;
