@@ -292,6 +292,11 @@ int plan_pieces(const Device& d, size_t n, size_t* bounds) {
         chunks = 1 + rest_chunks;
         bounds[1] = kLeadWaves * wave;
         for (int c = 1; c <= rest_chunks; c++) bounds[1 + c] = std::min(n, (kLeadWaves + rest * (size_t)c / rest_chunks) * wave);
+    } else if (max_chunks > 1 && n > wave) {
+        // one to four waves (the 1M block cut over 4 or 8 GPUs): a one-wave lead piece, the rest behind it -- the second
+        // upload and the first download overlap a kernel instead of being exposed
+        chunks = 2;
+        bounds[1] = wave;
     }
     bounds[chunks] = n;
     return chunks;
