@@ -3,7 +3,8 @@
 host C ABI; every recovered key / verdict is compared with the signer's key (known by construction from the generator --
 test infrastructure).  The once-in-2^31 fix-up paths of the field arithmetic are expected about three times per
 1M-signature secp256k1 batch (6.4e9 field operations), so this is also their at-scale check.
-   python tools/soak.py [rounds]   -> one line per batch, summary at the end"""
+   python tools/soak.py [rounds [first_round]]   -> one line per batch, summary at the end (first_round offsets the seeds
+   so that a later soak extends an earlier one instead of repeating it)"""
 import os
 import sys
 import time
@@ -16,11 +17,12 @@ import wgpu_sigops_b200 as w  # noqa: E402
 
 def main():
     rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    first = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     n = 1 << 20
     threads = coracle.host_threads()
     total = bad = 0
     t0 = time.time()
-    for r in range(rounds):
+    for r in range(first, first + rounds):
         seed = 0x50A40000 + r
         for cid, mod in ((0, w.secp256k1_ecdsa), (1, w.secp256r1_ecdsa)):
             s, m, pk = coracle.gen_ecdsa(cid, n, seed=seed, low_s=(r % 2 == 0), threads=threads)
