@@ -217,7 +217,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "sigs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "secp256k1 ecrecover, 1M-signature block (BASELINE config 4)",
+        "config": {"workload": "secp256k1 ecrecover, 1M-signature block per GPU (BASELINE config 4)",
                    "sample_per_step": sample, "note": "CPU arm: each step is a bounded sample of the workload"},
         "cpu_baseline": {"value": val, "unit": "sigs/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} random valid secp256k1 signatures per step, oracle/sigops_oracle.c, "
