@@ -24,7 +24,8 @@ def ecdsa_batch(cid, n, seed):
     sigs[q:2 * q, 32:] = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)  # valid r, random s / parity
     special = [0, 1, 2, 3, c.n - 2, c.n - 1, c.n, c.n + 1, c.p - 1, c.p, c.p + 1, 2**255 - 1, 2**255, 2**256 - 1,
                2**128, 2**224, 2**192 + 2**96, c.n // 2, c.n // 2 + 1, 7, c.gx]
-    for i in range(2 * q, min(3 * q, 2 * q + 6000)):  # special values in r, s or z
+    nsp = min(q // 2, 6000)
+    for i in range(2 * q, 2 * q + nsp):  # special values in r, s or z
         v = special[i % len(special)]
         where = (i // len(special)) % 3
         if where == 0:
@@ -34,8 +35,8 @@ def ecdsa_batch(cid, n, seed):
             sigs[i, 32] |= (i & 1) << 7
         else:
             msgs[i] = _be(v)
-    if 3 * q > 2 * q + 6000:  # the rest of that quarter: a valid signature with one flipped bit in r, s or z
-        idx = np.arange(2 * q + 6000, 3 * q)
+    if q > nsp:  # the rest of that quarter: a valid signature with one flipped bit in r, s or z
+        idx = np.arange(2 * q + nsp, 3 * q)
         bit = rng.integers(0, 8, size=len(idx)).astype(np.uint8)
         byte = rng.integers(0, 96, size=len(idx))
         for arr, lo in ((sigs, 0), (msgs, 64)):
@@ -58,7 +59,7 @@ def ed25519_batch(n, seed):
     sigs[2 * q:3 * q, 32:] = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)  # random s (mostly non-canonical)
     sigs[2 * q:3 * q:2, 63] &= 0x0F  # ... half of them canonical-range
     special = [0, 1, o.ED_P - 1, o.ED_P, o.ED_P + 1, 2**255 - 1, 2**255 - 19 + 2**255, 2**256 - 1, o.ED_L, o.ED_L - 1]
-    for i in range(3 * q, min(n, 3 * q + 3000)):  # special y in the key / R, special s
+    for i in range(3 * q, 3 * q + min(q // 2, 3000)):  # special y in the key / R, special s
         v = special[i % len(special)]
         le = np.frombuffer(int(v % 2**256).to_bytes(32, "little"), dtype=np.uint8)
         where = (i // len(special)) % 3

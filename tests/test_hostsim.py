@@ -65,3 +65,27 @@ def test_ed25519_logic():
     out = np.zeros(n, dtype=np.uint8)
     lib.hostsim_ed25519_verify(b"".join(x[1] for x in cases), b"".join(x[2] for x in cases), b"".join(x[3] for x in cases), n, out.ctypes.data)
     uc.check_ed_against_oracle(cases, out)
+
+
+def test_fuzz_builders_through_host_simulation():
+    """The mostly-invalid batches of tests/fuzz_cases.py (the GPU fuzz tests and tools/fuzz_soak.py use them at scale),
+    small, through the host-compiled kernel logic against the C oracle: rejections, bit flips and special values."""
+    import coracle
+    import fuzz_cases
+
+    lib = load_hostsim()
+    n = 4000
+    for cid in (0, 1):
+        sigs, msgs = fuzz_cases.ecdsa_batch(cid, n, seed=7)
+        exp_out, exp_st = coracle.ecrecover(cid, sigs, msgs)
+        out = np.zeros((n, 64), dtype=np.uint8)
+        st = np.zeros(n, dtype=np.uint8)
+        lib.hostsim_ecrecover(cid, sigs.tobytes(), msgs.tobytes(), n, out.ctypes.data, st.ctypes.data)
+        assert not (st != exp_st).any() and not (out != exp_out).any()
+        assert 0.1 < exp_st.mean() < 0.6
+    sigs, msgs, pks = fuzz_cases.ed25519_batch(n, seed=7)
+    exp = coracle.ecverify_ed25519(sigs, msgs, pks)
+    got = np.zeros(n, dtype=np.uint8)
+    lib.hostsim_ed25519_verify(sigs.tobytes(), msgs.tobytes(), pks.tobytes(), n, got.ctypes.data)
+    assert not (got != exp).any()
+    assert 0.05 < exp.mean() < 0.4
