@@ -9,8 +9,9 @@
  *
  * Conventions
  *   - all pointers are HOST pointers unless the name ends in `_device`; buffers are caller-owned;
- *   - every function is blocking (except `_device`, which is stream-ordered) and thread-safe
- *     (calls are serialised internally);
+ *   - every function is blocking (except `_device` and `sigops_queue_submit*`, which are stream-ordered) and
+ *     thread-safe: calls are serialised PER DEVICE (one host pipeline or one enqueue at a time on a device), so two
+ *     callers that use disjoint devices (sigops_batch_on_devices, queues, `_device`) run concurrently;
  *   - return value 0 = success; nonzero = CUDA / runtime failure, which the Rust shim maps to
  *     `Err(ShaderFailureError)` (src/lib.rs:12-14).  There is NO CPU fallback: without a usable
  *     CUDA device every compute entry point fails with a nonzero code and sigops_last_error()
@@ -45,6 +46,8 @@ extern "C" {
  * device on every API call; here the context (streams, device buffers, constant tables) persists.
  * device_ids == NULL or n_devices <= 0: use every visible CUDA device (or SIGOPS_GPUS=<count> of them).
  * Calling a compute entry point without sigops_init() initialises lazily with the defaults. */
+/* A second sigops_init with an explicit device list that differs from the pool's fails (nonzero): call
+ * sigops_shutdown() first.  sigops_init(NULL, 0) on an initialised pool is a no-op. */
 int sigops_init(const int* device_ids, int n_devices);
 int sigops_shutdown(void);
 int sigops_num_devices(void);
@@ -68,6 +71,19 @@ int sigops_secp256r1_ecrecover(const uint8_t* sigs, const uint8_t* msgs, size_t 
  * An undecodable public key yields 0 (dalek: VerifyingKey::from_bytes fails). */
 int sigops_ed25519_ecverify(const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n,
                             uint8_t* out_valid);
+
+/* The same three operations restricted to a subset of the pool: device_indices are positions in the pool (0 ..
+ * sigops_num_devices()-1, not CUDA ordinals), n_devices == 0 means the whole pool.  curve = SIGOPS_CURVE_*; pks is used by
+ * ed25519 only; out is n*64 bytes of keys (secp curves) or n verdict bytes (ed25519); out_status may be NULL.  Lets a
+ * multi-threaded verifier give every thread its own GPUs -- the reference can only serialise its callers on one adapter
+ * (`#[serial_test::serial]`, src/tests/secp256k1_ecdsa.rs:11-13; src/gpu.rs:7-14). */
+int sigops_batch_on_devices(int curve, const int* device_indices, int n_devices, const uint8_t* sigs, const uint8_t* msgs,
+                            const uint8_t* pks, size_t n, uint8_t* out, uint8_t* out_status);
+
+/* Failure semantics of every host-buffer entry point (src/secp256k1_ecdsa.rs:203-205: all-or-nothing): when a call returns
+ * nonzero every output buffer has been reset (keys / addresses / verdicts zero, status = SIGOPS_STATUS_INVALID), nothing the
+ * call enqueued is still in flight, and the pool stays usable.  SIGOPS_FAIL_DEVICE=<pool index> (environment, read per
+ * call) makes that device's shard fail with work in flight -- the fault-injection hook of the tests. */
 
 /* ed25519 with variable-length messages and optional strict semantics -- the form fuel_crypto::ed25519::verify needs
  * (ed25519-dalek `verify_strict` over arbitrary-length messages); the reference hard-wires 32-byte messages and the
@@ -98,7 +114,9 @@ int sigops_ecrecover_addresses(int curve, const uint8_t* sigs, const uint8_t* ms
  * (src/tests/mod.rs:134-149), x||y||t for ed25519 (src/tests/mod.rs:94-112).
  * log_limb_size must be in 11..=15 (src/wgsl/mont.wgsl:12,37).  *inout_len: capacity in u32 on entry,
  * number of u32 written on return (640 / 960 at log_limb_size = 13).  The engine itself never reads
- * these limbs (its own 32-bit tables are baked into the library). */
+ * these limbs (its own 32-bit tables are baked into the library).  Protocol: out == NULL (or *inout_len smaller than
+ * needed with out == NULL) returns 0 and stores the required length; out != NULL with too small a capacity returns nonzero
+ * and stores the required length. */
 int sigops_precompute_bases(int curve, uint32_t log_limb_size, uint32_t* out, size_t* inout_len);
 
 /* Shard planner used by the host entry points (pure host logic, no device needed): the batch is cut into
@@ -116,15 +134,18 @@ int sigops_last_timing(double* h2d_ms, double* kernel_ms, double* d2h_ms);
 uint64_t sigops_kernel_launches(void);
 
 /* Pinned host memory for callers that want zero-staging transfers (replaces the MAP_READ staging buffer of
- * src/gpu.rs:138-166).  Plain malloc'ed buffers are accepted everywhere too. */
+ * src/gpu.rs:138-166).  Plain malloc'ed (pageable) buffers are accepted everywhere too and are first-class: shards of
+ * 16,384 signatures or more go through the library's own pinned staging, filled and drained by per-device copy threads
+ * piece by piece under the kernels (SIGOPS_STAGING=0 disables it, SIGOPS_COPY_THREADS sets the threads per device). */
 void* sigops_host_alloc(size_t bytes);
 void sigops_host_free(void* p);
 
 /* Streaming service mode: a persistent ring of pre-registered pinned buffers instead of one
  * blocking call per batch.  Replaces, for a long-running verifier, the per-call device creation, buffer allocation and
  * blocking `device.poll(Maintain::Wait)` of src/gpu.rs:5-35,129-170.
- * A queue serves ONE operation (SIGOPS_CURVE_*) on ONE device of the pool (device_index = index into the pool, not a CUDA
- * ordinal) with `depth` slots of up to `max_batch` signatures each.  Every slot owns pinned host input / output arrays,
+ * A queue serves ONE operation (SIGOPS_CURVE_*) with `depth` slots of up to `max_batch` signatures each, on ONE device of the
+ * pool (device_index = index into the pool, not a CUDA ordinal) or, with device_index = -1, with its slots spread
+ * round-robin over every device of the pool (slot i lives on pool device i mod G: an 8-GPU verifier needs one queue).  Every slot owns pinned host input / output arrays,
  * device buffers, scratch and a CUDA stream; a slot's upload, fused kernel and download are replayed as one CUDA graph
  * while the request size repeats.  Slots in flight run concurrently on the device: small requests (a few thousand
  * signatures use one or two of the 16 resident warps per SM) overlap, so throughput scales with the number of slots in
@@ -133,7 +154,9 @@ void sigops_host_free(void* p);
  * points; `pks` is NULL unless the queue is ed25519; `status` is NULL for ed25519) -> sigops_queue_submit(slot, n)
  * (asynchronous; fails if the slot is still in flight or n > max_batch) -> sigops_queue_wait(slot) (blocks until that
  * request has completed) -> read `out` / `status` -> reuse the slot.  sigops_queue_poll() is the non-blocking test.
- * Thread-safe: several threads may drive different slots of one queue.  All queues must be destroyed before
+ * Thread-safe: several threads may drive different slots of one queue; one slot must not be waited on by two threads at
+ * once (the second wait fails).  A request that fails on the device is reported by sigops_queue_wait (nonzero) and the slot
+ * is released -- the queue is never wedged.  All queues must be destroyed before
  * sigops_shutdown().  SIGOPS_QUEUE_GRAPHS=0 disables graph replay (plain stream launches). */
 typedef struct sigops_queue sigops_queue;
 #define SIGOPS_QUEUE_MAX_DEPTH 64
@@ -142,6 +165,16 @@ int sigops_queue_destroy(sigops_queue* q);
 int sigops_queue_buffers(sigops_queue* q, int slot, uint8_t** sigs, uint8_t** msgs, uint8_t** pks, uint8_t** out,
                          uint8_t** status);
 int sigops_queue_submit(sigops_queue* q, int slot, size_t n);
+/* Device-resident producer: the request's inputs already live in the memory of CUDA device
+ * `src_device` (any device of the box, e.g. the GPU that produced or received the transactions).  They are moved into the
+ * slot's device buffers with cudaMemcpyPeerAsync -- over NVLink when the devices are peers -- on the slot's stream, followed
+ * by the kernel and the download of the results into the slot's pinned output arrays; the host never touches the inputs.
+ * ready_event (a cudaEvent_t, may be NULL): the slot's stream waits for it before copying (the producer's completion).
+ * Replaces the host-only upload path of src/gpu.rs:41-49. */
+int sigops_queue_submit_device(sigops_queue* q, int slot, const void* d_sigs, const void* d_msgs, const void* d_pks, size_t n,
+                               int src_device, void* ready_event);
+/* CUDA ordinal of the device a slot lives on (-1 on bad arguments). */
+int sigops_queue_slot_device(sigops_queue* q, int slot);
 int sigops_queue_poll(sigops_queue* q, int slot, int* done);
 /* n_done (may be NULL): size of the request that completed; device_ms (may be NULL): upload + kernel + download time of
  * that request on the device (CUDA events). */
@@ -151,7 +184,9 @@ int sigops_queue_info(sigops_queue* q, int* curve, int* device_index, size_t* ma
 
 /* Device-resident variants: inputs and outputs already live in the CURRENT CUDA device's memory
  * (16-byte aligned); the kernel is enqueued on `cuda_stream` (a cudaStream_t; NULL = default stream) and the
- * call returns without synchronising.  Used by bench.py for the kernel-only figure. */
+ * call returns without synchronising.  Launches that share a device's work tables are ordered behind one another with
+ * events, whatever streams they were enqueued on (two `_device` calls on different streams, or a `_device` call and a
+ * host-buffer call, never run on the same tables at once).  Used by bench.py for the kernel-only figure. */
 int sigops_secp256k1_ecrecover_device(const void* d_sigs, const void* d_msgs, size_t n, void* d_out_pubkeys,
                                       void* d_out_status, void* cuda_stream);
 int sigops_secp256r1_ecrecover_device(const void* d_sigs, const void* d_msgs, size_t n, void* d_out_pubkeys,

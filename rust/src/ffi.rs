@@ -23,6 +23,9 @@ extern "C" {
     pub fn sigops_queue_destroy(q: *mut SigopsQueue) -> c_int;
     pub fn sigops_queue_buffers(q: *mut SigopsQueue, slot: c_int, sigs: *mut *mut u8, msgs: *mut *mut u8, pks: *mut *mut u8, out: *mut *mut u8, status: *mut *mut u8) -> c_int;
     pub fn sigops_queue_submit(q: *mut SigopsQueue, slot: c_int, n: usize) -> c_int;
+    pub fn sigops_queue_submit_device(q: *mut SigopsQueue, slot: c_int, d_sigs: *const c_void, d_msgs: *const c_void, d_pks: *const c_void, n: usize, src_device: c_int, ready_event: *mut c_void) -> c_int;
+    pub fn sigops_queue_slot_device(q: *mut SigopsQueue, slot: c_int) -> c_int;
+    pub fn sigops_batch_on_devices(curve: c_int, device_indices: *const c_int, n_devices: c_int, sigs: *const u8, msgs: *const u8, pks: *const u8, n: usize, out: *mut u8, out_status: *mut u8) -> c_int;
     pub fn sigops_queue_poll(q: *mut SigopsQueue, slot: c_int, done: *mut c_int) -> c_int;
     pub fn sigops_queue_wait(q: *mut SigopsQueue, slot: c_int, n_done: *mut usize, device_ms: *mut f64) -> c_int;
     pub fn sigops_queue_info(q: *mut SigopsQueue, curve: *mut c_int, device_index: *mut c_int, max_batch: *mut usize, depth: *mut c_int, graph_launches: *mut u64, graph_captures: *mut u64) -> c_int;

@@ -12,6 +12,11 @@ from . import _lib
 MAX_SIGNATURES = 256 * 256 * 256 * 64  # src/secp256k1_ecdsa.rs:22
 
 
+class LengthMismatch(AssertionError, ValueError):
+    """The reference `assert!`s on these (src/secp256k1_ecdsa.rs:21-22, src/ed25519_eddsa.rs:22-24): callers that expect
+    the panic catch AssertionError; it is raised explicitly so that `python -O` cannot strip the check."""
+
+
 def check_compat_args(table_limbs: Optional[Sequence[int]], log_limb_size: int, expected_len_at_13: int) -> None:
     """`table_limbs` / `log_limb_size` are accepted for compatibility and validated, then ignored: the engine's own
     32-bit tables are baked into the library (BASELINE north_star)."""
@@ -28,8 +33,10 @@ def check_compat_args(table_limbs: Optional[Sequence[int]], log_limb_size: int, 
 
 def flatten(items: Sequence[bytes], width: int, what: str) -> np.ndarray:
     if isinstance(items, np.ndarray):
-        a = np.ascontiguousarray(items, dtype=np.uint8).reshape(-1, width)
-        return a
+        # no silent re-rowing or value casts: the array must already be n x width bytes
+        if items.dtype != np.uint8 or items.ndim != 2 or items.shape[1] != width:
+            raise ValueError(f"{what} array must have dtype uint8 and shape (n, {width}), got {items.dtype} {items.shape}")
+        return np.ascontiguousarray(items)
     for it in items:
         if len(it) != width:
             raise ValueError(f"{what} must be {width} bytes")
@@ -40,8 +47,11 @@ def ecrecover(entry: str, signatures, messages) -> Tuple[np.ndarray, np.ndarray]
     sigs = flatten(signatures, 64, "signature")
     msgs = flatten(messages, 32, "message")
     n = sigs.shape[0]
-    assert n == msgs.shape[0], "signatures and messages differ in length"  # src/secp256k1_ecdsa.rs:21
-    assert n <= MAX_SIGNATURES
+    # the reference panics here (assert!, src/secp256k1_ecdsa.rs:21-22); an exception that survives `python -O`
+    if n != msgs.shape[0]:
+        raise LengthMismatch("signatures and messages differ in length")
+    if n > MAX_SIGNATURES:
+        raise LengthMismatch("more than 2^30 signatures")
     out = np.zeros((n, 64), dtype=np.uint8)
     status = np.zeros(n, dtype=np.uint8)
     if n == 0:
@@ -56,8 +66,10 @@ def ecverify(signatures, messages, verifying_keys) -> np.ndarray:
     msgs = flatten(messages, 32, "message")
     pks = flatten(verifying_keys, 32, "verifying key")
     n = sigs.shape[0]
-    assert n == msgs.shape[0] == pks.shape[0]
-    assert n <= MAX_SIGNATURES
+    if not (n == msgs.shape[0] == pks.shape[0]):
+        raise LengthMismatch("signatures, messages and verifying keys differ in length")
+    if n > MAX_SIGNATURES:
+        raise LengthMismatch("more than 2^30 signatures")
     out = np.zeros(n, dtype=np.uint8)
     if n == 0:
         return out

@@ -20,7 +20,8 @@ SYMBOLS = [
     "sigops_test_unit", "sigops_test_unit_shape", "sigops_imad_peak", "sigops_plan_shards",
     "sigops_ed25519_ecverify_msgs", "sigops_sha256_batch", "sigops_ecrecover_addresses",
     "sigops_queue_create", "sigops_queue_destroy", "sigops_queue_buffers", "sigops_queue_submit", "sigops_queue_poll",
-    "sigops_queue_wait", "sigops_queue_info",
+    "sigops_queue_wait", "sigops_queue_info", "sigops_queue_submit_device", "sigops_queue_slot_device",
+    "sigops_batch_on_devices",
 ]
 
 _lib = None
@@ -74,6 +75,9 @@ def load() -> ctypes.CDLL:
     lib.sigops_queue_submit.argtypes = [vp, i32, sz]
     lib.sigops_queue_poll.argtypes = [vp, i32, c.POINTER(i32)]
     lib.sigops_queue_wait.argtypes = [vp, i32, c.POINTER(sz), c.POINTER(c.c_double)]
+    lib.sigops_queue_submit_device.argtypes = [vp, i32, vp, vp, vp, sz, i32, vp]
+    lib.sigops_queue_slot_device.argtypes = [vp, i32]
+    lib.sigops_batch_on_devices.argtypes = [i32, c.POINTER(i32), i32, vp, vp, vp, sz, vp, vp]
     lib.sigops_queue_info.argtypes = [vp, c.POINTER(i32), c.POINTER(i32), c.POINTER(sz), c.POINTER(i32),
                                       c.POINTER(c.c_uint64), c.POINTER(c.c_uint64)]
     _lib = lib

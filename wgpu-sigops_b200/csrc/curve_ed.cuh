@@ -45,7 +45,7 @@ namespace sigops {
     }
 
 #if defined(__CUDACC__)
-__device__ const u64 sha512_k_dev[80] = SG_SHA512_K;
+static __device__ const u64 sha512_k_dev[80] = SG_SHA512_K;
 #endif
 static const u64 sha512_k_host[80] = SG_SHA512_K;
 

@@ -1,0 +1,34 @@
+// Host-visible launchers of the kernels in kern_*.cu (one translation unit per kernel family so that the library builds in
+// parallel).  Every function returns a cudaError_t as int (0 = success).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace sigops {
+
+struct KLaunch {
+    int grid, tpb;
+    cudaStream_t stream;
+};
+
+int kl_k1_ecrecover(const KLaunch& l, const void* sigs, const void* msgs, size_t n, void* out, uint8_t* status, void* scratch,
+                    const uint32_t* gtab, uint32_t smem_words);
+int kl_r1_ecrecover(const KLaunch& l, const void* sigs, const void* msgs, size_t n, void* out, uint8_t* status, void* scratch,
+                    const uint32_t* gtab, uint32_t smem_words);
+int kl_k1_setup(int* max_blocks_per_sm);
+int kl_r1_setup(int* max_blocks_per_sm);
+int kl_ed_verify(const KLaunch& l, const void* sigs, const void* msgs, const void* pks, size_t n, uint8_t* valid, void* scratch,
+                 const uint32_t* btab, uint32_t smem_words);
+int kl_ed_verify_msgs(const KLaunch& l, const void* sigs, const uint8_t* msg_bytes, const unsigned long long* msg_off, const void* pks,
+                      size_t n, int strict, uint8_t* valid, void* scratch, const uint32_t* btab);
+int kl_ed_setup(int* max_blocks_per_sm, int* max_blocks_per_sm_msgs);
+int kl_sha256_msgs(cudaStream_t st, const uint8_t* bytes, const unsigned long long* off, size_t n, uint32_t* out);
+int kl_sha256_pubkeys(cudaStream_t st, const uint32_t* pubkeys, const uint8_t* status, size_t n, uint32_t* out);
+int kl_gen_tables(cudaStream_t st, uint32_t* k1tab, uint32_t* r1tab, uint32_t* edtab);
+int kl_unit(const KLaunch& l, int op, const uint32_t* in, size_t n, uint32_t* out, void* scratch, const uint32_t* k1g,
+            const uint32_t* r1g, const uint32_t* edb);
+int kl_unit_setup(int* max_blocks_per_sm);
+int kl_imad_peak(int kind, int grid, int block, cudaStream_t st, uint32_t* sink, int iters, uint32_t seed);
+
+}  // namespace sigops

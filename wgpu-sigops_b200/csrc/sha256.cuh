@@ -22,7 +22,7 @@ namespace sigops {
     }
 
 #if defined(__CUDACC__)
-__device__ const u32 sha256_k_dev[64] = SG_SHA256_K;
+static __device__ const u32 sha256_k_dev[64] = SG_SHA256_K;
 #endif
 static const u32 sha256_k_host[64] = SG_SHA256_K;
 

@@ -4,31 +4,44 @@
 // Replaces src/gpu.rs:5-170 (per-call wgpu device creation, storage/uniform buffers, pipeline creation from a WGSL
 // string, dispatch, staging-buffer read-back and device.destroy()) and the host halves of
 // src/secp256k1_ecdsa.rs:11-213, src/secp256r1_ecdsa.rs:12-214, src/ed25519_eddsa.rs:12-257 (flatten, zero-pad to a
-// power of two, five to seven dispatches, slice the padded result).  Here: no padding, one kernel launch per shard,
-// device context and buffers persist across calls, and there is no collective -- shards are independent
+// power of two, five to seven dispatches, slice the padded result).  Here: no padding, one kernel launch per piece of a
+// shard, device context and buffers persist across calls, and there is no collective -- shards are independent
 // (SURVEY.md 8e).  There is no CPU fallback: without a CUDA device every compute entry point returns nonzero.
+//
+// Concurrency model: the pool (device list) is guarded by a reader/writer lock -- compute calls hold it shared, init /
+// shutdown exclusively.  Every device has its own mutex (one host pipeline or one enqueue at a time per device), a
+// persistent worker thread that runs the device's shard of a multi-device call, and a few copy threads that move
+// pageable caller buffers through pinned staging.  Two callers on disjoint devices never wait for each other.
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <functional>
+#include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "kernels.cuh"
+#include "launch.h"
 
 using namespace sigops;
 
 namespace {
 
-std::mutex g_mu;      // serialises the entry points
-std::mutex g_err_mu;  // shard threads may report errors concurrently
+std::shared_mutex g_pool_mu;  // shared: compute calls; exclusive: init / shutdown
+std::mutex g_err_mu;          // shard threads may report errors concurrently
 std::string g_err;
 std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_call_seq{0};
+thread_local uint64_t t_last_call = 0;  // sigops_last_timing reports the calling thread's last host-buffer call
 thread_local bool t_capturing = false;  // stream capture records a launch, it does not perform one
 
 void set_err(const std::string& s) {
@@ -38,7 +51,7 @@ void set_err(const std::string& s) {
 
 #define CK(call)                                                                                       \
     do {                                                                                               \
-        cudaError_t e_ = (call);                                                                       \
+        cudaError_t e_ = (cudaError_t)(call);                                                          \
         if (e_ != cudaSuccess) {                                                                       \
             char b_[512];                                                                              \
             snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
@@ -47,12 +60,45 @@ void set_err(const std::string& s) {
         }                                                                                              \
     } while (0)
 
+// counts outstanding jobs; wait() blocks until all are done
+struct Counter {
+    std::mutex mu;
+    std::condition_variable cv;
+    size_t pending = 0;
+    void add(size_t k) {
+        std::lock_guard<std::mutex> lk(mu);
+        pending += k;
+    }
+    void done() {
+        std::lock_guard<std::mutex> lk(mu);
+        if (--pending == 0) cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return pending == 0; });
+    }
+};
+
+struct CopyJob {
+    void* dst;
+    const void* src;
+    size_t bytes;
+    Counter* c;
+};
+
+constexpr int kMaxChunks = 8;
+
 struct Device {
-    int id = -1;
+    int id = -1;     // CUDA ordinal
+    int index = -1;  // position in the pool
     int sms = 0;
+    std::mutex mu;   // one host pipeline / one enqueue at a time on this device
+    std::atomic<int> inflight{0};
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;  // kernels / uploads / downloads
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_in[8] = {}, ev_k[8] = {};
+    cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_down[kMaxChunks] = {};
+    cudaEvent_t scratch_ev = nullptr;  // last launch that used `scratch`: the next one (any stream) waits for it
+    bool scratch_used = false;
     // device buffers (grow-only)
     uint8_t* d_in = nullptr;
     size_t in_cap = 0;
@@ -60,14 +106,105 @@ struct Device {
     size_t out_cap = 0;
     Q4* scratch = nullptr;
     size_t scratch_cap = 0;  // in Q4
+    // pinned staging for pageable caller buffers (grow-only)
+    uint8_t* h_in = nullptr;
+    size_t h_in_cap = 0;
+    uint8_t* h_out = nullptr;
+    size_t h_out_cap = 0;
     const u32 *k1g = nullptr, *r1g = nullptr, *edb = nullptr;
     int grid_k1 = 0, grid_r1 = 0, grid_ed = 0, grid_edm = 0, grid_unit = 0;
     float ms_h2d = 0, ms_kernel = 0, ms_d2h = 0;
+    uint64_t last_call = 0;
     bool smem_tables = true;  // SIGOPS_SMEM_TABLES=0 leaves the fixed-base tables in L2
+    // persistent worker: runs this device's shard of a multi-device call (no std::thread spawn / join per call)
+    std::thread worker;
+    std::mutex wmu;
+    std::condition_variable wcv;
+    std::deque<std::function<void()>> wq;
+    bool wstop = false;
+    // copy threads: pageable caller memory <-> pinned staging
+    std::vector<std::thread> copiers;
+    std::mutex cmu;
+    std::condition_variable ccv;
+    std::deque<CopyJob> cq;
+    bool cstop = false;
+
+    void post(std::function<void()> f) {
+        {
+            std::lock_guard<std::mutex> lk(wmu);
+            wq.push_back(std::move(f));
+        }
+        wcv.notify_one();
+    }
+    void worker_main() {
+        cudaSetDevice(id);
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> lk(wmu);
+                wcv.wait(lk, [&] { return wstop || !wq.empty(); });
+                if (wq.empty()) return;
+                f = std::move(wq.front());
+                wq.pop_front();
+            }
+            f();
+        }
+    }
+    // copy [src, src + bytes) to dst in slices of at most kCopySlice, spread over the copy threads
+    static constexpr size_t kCopySlice = (size_t)1 << 20;
+    void post_copy(void* dst, const void* src, size_t bytes, Counter* c) {
+        if (bytes == 0) return;
+        const size_t slices = (bytes + kCopySlice - 1) / kCopySlice;
+        c->add(slices);
+        {
+            std::lock_guard<std::mutex> lk(cmu);
+            for (size_t s = 0; s < slices; s++) {
+                const size_t off = s * kCopySlice;
+                cq.push_back({(uint8_t*)dst + off, (const uint8_t*)src + off, std::min(kCopySlice, bytes - off), c});
+            }
+        }
+        ccv.notify_all();
+    }
+    void copier_main() {
+        for (;;) {
+            CopyJob j;
+            {
+                std::unique_lock<std::mutex> lk(cmu);
+                ccv.wait(lk, [&] { return cstop || !cq.empty(); });
+                if (cq.empty()) return;
+                j = cq.front();
+                cq.pop_front();
+            }
+            memcpy(j.dst, j.src, j.bytes);
+            j.c->done();
+        }
+    }
+    void stop_threads() {
+        {
+            std::lock_guard<std::mutex> lk(wmu);
+            wstop = true;
+        }
+        wcv.notify_all();
+        if (worker.joinable()) worker.join();
+        {
+            std::lock_guard<std::mutex> lk(cmu);
+            cstop = true;
+        }
+        ccv.notify_all();
+        for (auto& t : copiers)
+            if (t.joinable()) t.join();
+        copiers.clear();
+    }
 };
 
-std::vector<Device> g_dev;
-bool g_inited = false;
+// The pool is heap-allocated and never destroyed at process exit (its threads may still be parked on their condition
+// variables when static destructors run); sigops_shutdown() tears it down explicitly.
+std::vector<std::unique_ptr<Device>>& pool() {
+    static auto* p = new std::vector<std::unique_ptr<Device>>();
+    return *p;
+}
+std::atomic<bool> g_inited{false};
+std::vector<int> g_ids;  // CUDA ordinals the pool was initialised with
 
 int ensure_buf(uint8_t** p, size_t* cap, size_t need) {
     if (need <= *cap) return 0;
@@ -80,27 +217,57 @@ int ensure_buf(uint8_t** p, size_t* cap, size_t need) {
     return 0;
 }
 
+int ensure_pinned(uint8_t** p, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) CK(cudaFreeHost(*p));
+    *p = nullptr;
+    *cap = 0;
+    size_t want = need + need / 4 + 4096;
+    CK(cudaHostAlloc((void**)p, want, cudaHostAllocPortable));
+    *cap = want;
+    return 0;
+}
+
 int ensure_scratch(Device& d, size_t q4s) {
     if (q4s <= d.scratch_cap) return 0;
-    if (d.scratch) CK(cudaFree(d.scratch));
+    if (d.scratch) CK(cudaFree(d.scratch));  // cudaFree synchronises the device: no launch still uses the old scratch
     d.scratch = nullptr;
     d.scratch_cap = 0;
+    d.scratch_used = false;
     CK(cudaMalloc((void**)&d.scratch, q4s * sizeof(Q4)));
     d.scratch_cap = q4s;
     return 0;
 }
 
-template <class K>
-int max_grid(Device& d, K kernel, int* out) {
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0));
-    if (per_sm < 1) per_sm = 1;
-    *out = per_sm * d.sms;
-    return 0;
+void free_device(Device& d) {
+    d.stop_threads();
+    if (d.id < 0) return;
+    cudaSetDevice(d.id);
+    if (d.d_in) cudaFree(d.d_in);
+    if (d.d_out) cudaFree(d.d_out);
+    if (d.scratch) cudaFree(d.scratch);
+    if (d.h_in) cudaFreeHost(d.h_in);
+    if (d.h_out) cudaFreeHost(d.h_out);
+    if (d.k1g) cudaFree((void*)d.k1g);
+    if (d.r1g) cudaFree((void*)d.r1g);
+    if (d.edb) cudaFree((void*)d.edb);
+    for (auto& e : d.ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : d.ev_in)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : d.ev_k)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : d.ev_down)
+        if (e) cudaEventDestroy(e);
+    if (d.scratch_ev) cudaEventDestroy(d.scratch_ev);
+    if (d.stream) cudaStreamDestroy(d.stream);
+    if (d.s_in) cudaStreamDestroy(d.s_in);
+    if (d.s_out) cudaStreamDestroy(d.s_out);
 }
 
-int init_device(Device& d, int id) {
+int init_device(Device& d, int id, int index, int copy_threads) {
     d.id = id;
+    d.index = index;
     CK(cudaSetDevice(id));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, id));
@@ -118,32 +285,37 @@ int init_device(Device& d, int id) {
     for (auto& e : d.ev) CK(cudaEventCreate(&e));
     for (auto& e : d.ev_in) CK(cudaEventCreateWithFlags(&e, cudaEventDefault));
     for (auto& e : d.ev_k) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : d.ev_down) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&d.scratch_ev, cudaEventDisableTiming));
     // fixed-base tables: computed on the device once, resident for the life of the context (L2-sized: 576 KB)
     u32 *k1t = nullptr, *r1t = nullptr, *edt = nullptr;
     CK(cudaMalloc((void**)&k1t, (size_t)2 * kGTabEntries * 16 * sizeof(u32)));
+    d.k1g = k1t;
     CK(cudaMalloc((void**)&r1t, (size_t)kGTabEntries * 16 * sizeof(u32)));
+    d.r1g = r1t;
     CK(cudaMalloc((void**)&edt, (size_t)kGTabEntries * 24 * sizeof(u32)));
-    gen_tables_kernel<<<(kGTabEntries + 63) / 64, 64, 0, d.stream>>>(k1t, r1t, edt);
-    CK(cudaGetLastError());
+    d.edb = edt;
+    CK(kl_gen_tables(d.stream, k1t, r1t, edt));
     CK(cudaStreamSynchronize(d.stream));
     g_launches++;
-    d.k1g = k1t;
-    d.r1g = r1t;
-    d.edb = edt;
     if (const char* e = getenv("SIGOPS_SMEM_TABLES")) d.smem_tables = atoi(e) != 0;
-    CK(cudaFuncSetAttribute(ecrecover_kernel<CurveK1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGTabEntries * 16 * 4));
-    CK(cudaFuncSetAttribute(ecrecover_kernel<CurveR1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGTabEntries * 16 * 4));
-    CK(cudaFuncSetAttribute(ed25519_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGTabEntries * 24 * 4));
-    if (max_grid(d, ecrecover_kernel<CurveK1>, &d.grid_k1)) return 1;
-    if (max_grid(d, ecrecover_kernel<CurveR1>, &d.grid_r1)) return 1;
-    if (max_grid(d, ed25519_verify_kernel, &d.grid_ed)) return 1;
-    if (max_grid(d, ed25519_verify_msgs_kernel, &d.grid_edm)) return 1;
-    if (max_grid(d, unit_kernel, &d.grid_unit)) return 1;
+    int per_sm = 0, per_sm2 = 0;
+    CK(kl_k1_setup(&per_sm));
+    d.grid_k1 = std::max(per_sm, 1) * d.sms;
+    CK(kl_r1_setup(&per_sm));
+    d.grid_r1 = std::max(per_sm, 1) * d.sms;
+    CK(kl_ed_setup(&per_sm, &per_sm2));
+    d.grid_ed = std::max(per_sm, 1) * d.sms;
+    d.grid_edm = std::max(per_sm2, 1) * d.sms;
+    CK(kl_unit_setup(&per_sm));
+    d.grid_unit = std::max(per_sm, 1) * d.sms;
+    d.worker = std::thread([&d] { d.worker_main(); });
+    for (int i = 0; i < copy_threads; i++) d.copiers.emplace_back([&d] { d.copier_main(); });
     return 0;
 }
 
-int do_init(const int* ids, int n) {
-    if (g_inited) return 0;
+// caller holds g_pool_mu exclusively
+int do_init_locked(const int* ids, int n) {
     // The streaming mode keeps many small launches in flight on separate streams; with the default of 8 hardware work
     // queues no more than ~4 requests overlap and further submits block in the driver (measured: profiles/r01_queue_sweep.json).
     // Only effective if this process has not created its CUDA context yet; an explicit setting wins.
@@ -162,6 +334,10 @@ int do_init(const int* ids, int n) {
                 set_err("sigops_init: device id out of range");
                 return 1;
             }
+            if (std::find(use.begin(), use.end(), ids[i]) != use.end()) {
+                set_err("sigops_init: duplicate device id");
+                return 1;
+            }
             use.push_back(ids[i]);
         }
     } else {
@@ -172,60 +348,99 @@ int do_init(const int* ids, int n) {
         }
         for (int i = 0; i < want; i++) use.push_back(i);
     }
-    g_dev.assign(use.size(), Device());
-    for (size_t i = 0; i < use.size(); i++)
-        if (init_device(g_dev[i], use[i])) {
-            g_dev.clear();
+    if (g_inited.load()) {
+        // already up: an explicit device list must match the pool (a silent no-op would leave the caller believing it had
+        // pinned devices it has not); lazy / default initialisation is always satisfied by the existing pool
+        if (ids && n > 0 && use != g_ids) {
+            set_err("sigops_init: the pool is already initialised with a different device set; call sigops_shutdown() first");
             return 1;
         }
-    g_inited = true;
+        return 0;
+    }
+    int copy_threads = 0;
+    if (const char* s = getenv("SIGOPS_COPY_THREADS")) copy_threads = atoi(s);
+    if (copy_threads <= 0) {
+        const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+        copy_threads = std::max(1, std::min(4, hw / (2 * (int)use.size())));
+    }
+    auto& P = pool();
+    P.clear();
+    for (size_t i = 0; i < use.size(); i++) {
+        P.emplace_back(new Device());
+        if (init_device(*P.back(), use[i], (int)i, copy_threads)) {
+            for (auto& d : P) free_device(*d);  // release what the devices initialised so far hold
+            P.clear();
+            return 1;
+        }
+    }
+    g_ids = use;
+    g_inited.store(true);
     return 0;
 }
 
-// device context for the CURRENT device (used by the *_device entry points and the test shims)
+// lazy initialisation with the defaults; cheap once the pool is up
+int ensure_init() {
+    if (g_inited.load()) return 0;
+    std::unique_lock<std::shared_mutex> lk(g_pool_mu);
+    return do_init_locked(nullptr, 0);
+}
+
+// device context for the CURRENT device (used by the *_device entry points); caller holds the pool lock (shared)
 Device* current_device() {
     int cur = 0;
     if (cudaGetDevice(&cur) != cudaSuccess) return nullptr;
-    for (auto& d : g_dev)
-        if (d.id == cur) return &d;
+    for (auto& d : pool())
+        if (d->id == cur) return d.get();
     return nullptr;
 }
 
 enum Op { OP_K1 = 0, OP_R1 = 1, OP_ED = 2 };
 
-// Launch geometry: full 512-thread blocks (one per SM, all 16 warps phase-locked by the kernels' barriers) once the batch
-// covers the device; smaller batches are spread over all SMs with proportionally smaller blocks instead of filling
-// a few SMs to the brim (latency of the 64 ... 64k end of the batch-size sweep).
+int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+// Launch geometry.  One signature per thread per pass; a launch of n signatures runs P = ceil(n / (SMs x 512)) passes, and
+// the block size is BALANCED over them: tpb = ceil(n / (SMs x P)) rounded up to a warp, one block per SM.  A pass costs
+// about the same whether 12 or 16 warps per SM run it, so 1.73 waves run as two passes of 14 warps (and share their
+// inversions, curve_sw.cuh) instead of one full pass plus a 73%-empty one.  Small batches (P = 1) are spread over all SMs
+// with proportionally smaller blocks instead of filling a few SMs to the brim (latency of the 64 ... 64k end of the sweep).
+// SIGOPS_BALANCED=0 restores round 1's geometry (full 512-thread blocks once the batch covers the device).
 void launch_geometry(const Device& d, Op op, size_t n, int* grid, int* tpb_out) {
     const int max_g = op == OP_K1 ? d.grid_k1 : op == OP_R1 ? d.grid_r1 : d.grid_ed;
+    const size_t wave = (size_t)d.sms * kBlock;
     int tpb = kBlock;
-    if (n < (size_t)d.sms * kBlock) {
+    size_t passes = 1;
+    if (n < wave) {
         size_t per_sm = (n + d.sms - 1) / d.sms;
         tpb = (int)std::min<size_t>(kBlock, std::max<size_t>(32, (per_sm + 31) / 32 * 32));
+    } else if (env_int("SIGOPS_BALANCED", 1) != 0) {
+        passes = (n + wave - 1) / wave;
+        size_t per_sm = (n + (size_t)d.sms * passes - 1) / ((size_t)d.sms * passes);
+        tpb = (int)std::min<size_t>(kBlock, std::max<size_t>(32, (per_sm + 31) / 32 * 32));
     }
-    size_t blocks = (n + tpb - 1) / tpb;
+    size_t blocks = (n + (size_t)tpb * passes - 1) / ((size_t)tpb * passes);
+    if (passes == 1) blocks = (n + tpb - 1) / tpb;
     *grid = (int)std::min<size_t>(blocks, (size_t)max_g);
     *tpb_out = tpb;
 }
 
-// The kernels index their per-thread scratch by global thread id: `scratch` must hold chunks x grid x tpb Q4 and must not
-// be shared by two launches that may run concurrently.
-// A launch of w.f waves (one wave = SMs x 512 signatures, one per thread) costs ceil(w.f) full passes of ~1.65 ms: the last,
-// partial pass runs every thread (rows past the end are clamped) at 16 warps per SM.  When the tail is at most
-// kTailSplitNum/kTailSplitDen of a wave it is launched on its own right behind the main part, with the small-batch
-// geometry: fewer warps per SM finish a pass sooner (0.85 ms at one warp per scheduler).  Matters for shards of one to a
-// few waves -- the 1M block cut over 4 or 8 GPUs, the middle of the batch-size sweep.
+// Round 1's alternative for shards of w.f waves: launch the partial wave on its own behind the whole ones
+// (SIGOPS_TAIL_SPLIT=1; off by default since the balanced geometry above covers the case in one launch).
 constexpr size_t kTailSplitNum = 3, kTailSplitDen = 4;
 size_t tail_split(const Device& d, size_t n) {  // signatures in the main launch (n if no split)
     const size_t wave = (size_t)d.sms * kBlock;
     if (n < wave) return n;
+    if (env_int("SIGOPS_TAIL_SPLIT", 0) == 0) return n;
     const size_t tail = n % wave;
     if (tail == 0 || tail * kTailSplitDen > wave * kTailSplitNum) return n;
-    if (const char* e = getenv("SIGOPS_TAIL_SPLIT"))
-        if (atoi(e) == 0) return n;
     return n - tail;
 }
 
+// The kernels index their per-thread scratch by global thread id: `scratch` must hold chunks x grid x tpb Q4 and must not
+// be shared by two launches that may run concurrently (launch_op orders the users of the per-device scratch with an event;
+// queue slots own theirs).
 int launch_op_scratch(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_msgs, const uint8_t* d_pks, size_t n,
                       uint8_t* d_out, uint8_t* d_status, Q4* scratch, cudaStream_t st) {
     if (n == 0) return 0;
@@ -236,87 +451,93 @@ int launch_op_scratch(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_
         return launch_op_scratch(d, op, d_sigs + main_n * 64, d_msgs + main_n * 32, d_pks ? d_pks + main_n * 32 : nullptr,
                                  n - main_n, d_out + main_n * os, d_status ? d_status + main_n : nullptr, scratch, st);
     }
-    int grid, tpb;
-    launch_geometry(d, op, n, &grid, &tpb);
+    KLaunch l;
+    l.stream = st;
+    launch_geometry(d, op, n, &l.grid, &l.tpb);
     // stage the fixed-base table in shared memory when the launch is big enough to amortise the copy (>= 1 full pass)
-    const bool stage = d.smem_tables && n >= (size_t)d.sms * kBlock && tpb == kBlock;
+    const bool stage = d.smem_tables && n >= (size_t)d.sms * kBlock;
     const u32 sw_words = stage ? (u32)kGTabEntries * 16 : 0, ed_words = stage ? (u32)kGTabEntries * 24 : 0;
     switch (op) {
-        case OP_K1:
-            ecrecover_kernel<CurveK1><<<grid, tpb, sw_words * 4, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, n, (Q4*)d_out,
-                                                                       d_status, scratch, d.k1g, sw_words);
-            break;
-        case OP_R1:
-            ecrecover_kernel<CurveR1><<<grid, tpb, sw_words * 4, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, n, (Q4*)d_out,
-                                                                       d_status, scratch, d.r1g, sw_words);
-            break;
-        case OP_ED:
-            ed25519_verify_kernel<<<grid, tpb, ed_words * 4, st>>>((const Q4*)d_sigs, (const Q4*)d_msgs, (const Q4*)d_pks, n,
-                                                                   d_out, scratch, d.edb, ed_words);
-            break;
+        case OP_K1: CK(kl_k1_ecrecover(l, d_sigs, d_msgs, n, d_out, d_status, scratch, d.k1g, sw_words)); break;
+        case OP_R1: CK(kl_r1_ecrecover(l, d_sigs, d_msgs, n, d_out, d_status, scratch, d.r1g, sw_words)); break;
+        case OP_ED: CK(kl_ed_verify(l, d_sigs, d_msgs, d_pks, n, d_out, scratch, d.edb, ed_words)); break;
     }
-    CK(cudaGetLastError());
     if (!t_capturing) g_launches++;
     return 0;
 }
 
+// launch on the per-device scratch: every such launch waits for the previous one (whatever stream that was enqueued on),
+// so a *_device call on a caller's stream can never overlap a host-buffer call or another *_device call on the same tables
 int launch_op(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_msgs, const uint8_t* d_pks, size_t n,
               uint8_t* d_out, uint8_t* d_status, cudaStream_t st) {
     if (n == 0) return 0;
     const int max_g = op == OP_K1 ? d.grid_k1 : op == OP_R1 ? d.grid_r1 : d.grid_ed;
     const size_t chunks = op == OP_ED ? kEdBatchChunks : kSwBatchChunks;
     if (ensure_scratch(d, chunks * (size_t)max_g * kBlock)) return 1;
-    return launch_op_scratch(d, op, d_sigs, d_msgs, d_pks, n, d_out, d_status, d.scratch, st);
+    if (d.scratch_used) CK(cudaStreamWaitEvent(st, d.scratch_ev, 0));
+    if (launch_op_scratch(d, op, d_sigs, d_msgs, d_pks, n, d_out, d_status, d.scratch, st)) return 1;
+    CK(cudaEventRecord(d.scratch_ev, st));
+    d.scratch_used = true;
+    return 0;
 }
 
 // One shard on one device.  The shard is cut into up to kMaxChunks pieces that flow through a three-stage pipeline
-// (H2D on s_in, kernel on stream, D2H on s_out, chained with events), so that with pinned host buffers only the first
-// piece's upload and the last piece's download are exposed.  Kernels run back to back on ONE stream: they share the
-// per-thread scratch tables.
-constexpr int kMaxChunks = 8;
+// (H2D on s_in, kernel on stream, D2H on s_out, chained with events), so that only the first piece's upload and the last
+// piece's download are exposed.  Kernels run back to back on ONE stream: they share the per-thread scratch tables.
 constexpr size_t kLeadWaves = 2;  // passes in the first, short piece (~4 ms of kernel): exposed upload ~0.3 ms
+constexpr size_t kTailWaves = 2;  // and in the last one: exposed download ~0.2 ms instead of ~0.6 ms
 
 // Piece plan: pieces are whole multiples of one wave (SMs x 512 threads, one signature per thread per pass) so that only
-// the last piece ends on a partial wave.  The first piece is short (kLeadWaves) so that the kernels start early; the rest
-// is cut into equal pieces of at most kSwBatch waves -- one full shared-inversion batch per thread (curve_sw.cuh).
+// the last piece ends on a partial wave.  The first and the last piece are short so that the kernels start early and the
+// final download is small; the rest is cut into equal pieces of at most kSwBatch waves -- one full shared-inversion batch
+// per thread (curve_sw.cuh).
 int plan_pieces(const Device& d, size_t n, size_t* bounds) {
-    int max_chunks = kMaxChunks;
-    if (const char* e = getenv("SIGOPS_MAX_CHUNKS")) max_chunks = std::max(1, std::min(kMaxChunks, atoi(e)));
+    int max_chunks = std::max(1, std::min(kMaxChunks, env_int("SIGOPS_MAX_CHUNKS", kMaxChunks)));
     const size_t wave = (size_t)d.sms * kBlock;
     const size_t n_waves = (n + wave - 1) / wave;
     int chunks = 1;
     bounds[0] = 0;
     if (max_chunks > 1 && n_waves >= 2 * kLeadWaves + 1) {
-        const size_t rest = n_waves - kLeadWaves;
-        const int rest_chunks = (int)std::min<size_t>((size_t)max_chunks - 1, (rest + kSwBatch - 1) / kSwBatch);
-        chunks = 1 + rest_chunks;
+        size_t rest = n_waves - kLeadWaves;
+        const bool tail = max_chunks > 2 && rest >= kTailWaves + 2;
+        if (tail) rest -= kTailWaves;
+        const int rest_chunks =
+            (int)std::min<size_t>((size_t)max_chunks - 1 - (tail ? 1 : 0), (rest + kSwBatch - 1) / kSwBatch);
         bounds[1] = kLeadWaves * wave;
         for (int c = 1; c <= rest_chunks; c++) bounds[1 + c] = std::min(n, (kLeadWaves + rest * (size_t)c / rest_chunks) * wave);
+        chunks = 1 + rest_chunks + (tail ? 1 : 0);
     } else if (max_chunks > 1 && n > wave) {
-        // one to four waves (the 1M block cut over 4 or 8 GPUs): a one-wave lead piece, the rest behind it -- the second
-        // upload and the first download overlap a kernel instead of being exposed
+        // one to four waves (the 1M block cut over 4 or 8 GPUs): two pieces of whole waves, the first one the smaller --
+        // the second upload and the first download overlap a kernel instead of being exposed
         chunks = 2;
-        bounds[1] = wave;
+        bounds[1] = std::max<size_t>(1, n_waves / 2) * wave;
     }
     bounds[chunks] = n;
     return chunks;
 }
 
-// The three-stage pipeline over the pieces of one shard.  up(lo, m, stream) enqueues the uploads of piece [lo, lo + m),
-// launch(lo, m, stream) its kernels, down(lo, m, stream) its downloads; each returns nonzero on failure.
-template <class Up, class Launch, class Down>
-int run_pipeline(Device& d, size_t n, Up up, Launch launch, Down down) {
+// The three-stage pipeline over the pieces of one shard.  up(c, lo, m, stream) enqueues the uploads of piece c = [lo, lo + m),
+// launch(c, lo, m, stream) its kernels, down(c, lo, m, stream) its downloads; post(c, lo, m) runs on the host once piece c's
+// downloads have completed (staged path: copy out of the pinned staging).  Each returns nonzero on failure.
+template <class Up, class Launch, class Down, class Post>
+int run_pipeline_body(Device& d, size_t n, bool inject_fail, bool has_post, Up up, Launch launch, Down down, Post post) {
     size_t bounds[kMaxChunks + 1];
     const int chunks = plan_pieces(d, n, bounds);
     CK(cudaEventRecord(d.ev[0], d.s_in));
     for (int c = 0; c < chunks; c++) {
         const size_t lo = bounds[c], m = bounds[c + 1] - lo;
-        if (up(lo, m, d.s_in)) return 1;
+        if (up(c, lo, m, d.s_in)) return 1;
         CK(cudaEventRecord(d.ev_in[c], d.s_in));
         CK(cudaStreamWaitEvent(d.stream, d.ev_in[c], 0));
         if (c == 0) CK(cudaEventRecord(d.ev[1], d.stream));
-        if (launch(lo, m, d.stream)) return 1;
+        if (launch(c, lo, m, d.stream)) return 1;
         CK(cudaEventRecord(d.ev_k[c], d.stream));
+        if (inject_fail && c == 0) {  // fault injection: fail with work in flight on all three streams
+            char b[128];
+            snprintf(b, sizeof b, "injected failure on pool device %d (SIGOPS_FAIL_DEVICE)", d.index);
+            set_err(b);
+            return 1;
+        }
     }
     CK(cudaEventRecord(d.ev[2], d.stream));
     // downloads are enqueued after every upload and kernel: a download into pageable memory blocks the calling thread
@@ -324,9 +545,15 @@ int run_pipeline(Device& d, size_t n, Up up, Launch launch, Down down) {
     for (int c = 0; c < chunks; c++) {
         const size_t lo = bounds[c], m = bounds[c + 1] - lo;
         CK(cudaStreamWaitEvent(d.s_out, d.ev_k[c], 0));
-        if (down(lo, m, d.s_out)) return 1;
+        if (down(c, lo, m, d.s_out)) return 1;
+        if (has_post) CK(cudaEventRecord(d.ev_down[c], d.s_out));
     }
     CK(cudaEventRecord(d.ev[3], d.s_out));
+    if (has_post)
+        for (int c = 0; c < chunks; c++) {
+            CK(cudaEventSynchronize(d.ev_down[c]));
+            if (post(c, bounds[c], bounds[c + 1] - bounds[c])) return 1;
+        }
     CK(cudaStreamSynchronize(d.s_out));
     CK(cudaStreamSynchronize(d.stream));
     CK(cudaStreamSynchronize(d.s_in));
@@ -339,8 +566,40 @@ int run_pipeline(Device& d, size_t n, Up up, Launch launch, Down down) {
     return 0;
 }
 
+// Error discipline: whatever fails inside, nothing enqueued by this call may still read or write the caller's buffers (or
+// the device's) once the API has returned -- drain the three streams and clear the sticky error state first.
+template <class Up, class Launch, class Down, class Post>
+int run_pipeline(Device& d, size_t n, bool inject_fail, bool has_post, Up up, Launch launch, Down down, Post post) {
+    const int rc = run_pipeline_body(d, n, inject_fail, has_post, up, launch, down, post);
+    if (rc) {
+        cudaStreamSynchronize(d.s_in);
+        cudaStreamSynchronize(d.stream);
+        cudaStreamSynchronize(d.s_out);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
+template <class Up, class Launch, class Down>
+int run_pipeline(Device& d, size_t n, bool inject_fail, Up up, Launch launch, Down down) {
+    return run_pipeline(d, n, inject_fail, false, up, launch, down, [](int, size_t, size_t) { return 0; });
+}
+
+// is this host pointer ordinary pageable memory (neither cudaHostAlloc'ed nor cudaHostRegister'ed)?
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+// Below this many signatures a pageable shard is copied directly (the driver stages small copies itself at no cost)
+constexpr size_t kMinStaged = 16384;
+
 int run_shard(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n, uint8_t* out,
-              uint8_t* status) {
+              uint8_t* status, bool inject_fail) {
     CK(cudaSetDevice(d.id));
     const size_t in_bytes = n * (op == OP_ED ? 128 : 96);
     const size_t out_stride = op == OP_ED ? 1 : 64;
@@ -351,39 +610,87 @@ int run_shard(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs, const 
     uint8_t* d_msgs = d.d_in + n * 64;
     uint8_t* d_pks = d.d_in + n * 96;
     uint8_t* d_status = op == OP_ED ? nullptr : d.d_out + n * 64;
-    auto up = [&](size_t lo, size_t m, cudaStream_t st) -> int {
-        CK(cudaMemcpyAsync(d_sigs + lo * 64, sigs + lo * 64, m * 64, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(d_msgs + lo * 32, msgs + lo * 32, m * 32, cudaMemcpyHostToDevice, st));
-        if (op == OP_ED) CK(cudaMemcpyAsync(d_pks + lo * 32, pks + lo * 32, m * 32, cudaMemcpyHostToDevice, st));
+    // Pageable caller buffers (what `&Vec<...>` hands over, src/secp256k1_ecdsa.rs:61-66) go through pinned staging filled
+    // / drained by the device's copy threads, piece by piece, so that the DMA engines run at pinned speed and the host
+    // copies overlap the kernels; replaces the create_buffer_init upload / MAP_READ staging of src/gpu.rs:41-49,138-166.
+    const int staging = env_int("SIGOPS_STAGING", -1);  // -1 auto, 0 never, 1 always
+    const bool big = n >= kMinStaged || staging == 1;
+    const bool stage_in = staging != 0 && big && (staging == 1 || is_pageable(sigs) || is_pageable(msgs) || (pks && is_pageable(pks)));
+    const bool stage_out = staging != 0 && big && (staging == 1 || is_pageable(out) || (status && is_pageable(status)));
+    if (stage_in && ensure_pinned(&d.h_in, &d.h_in_cap, in_bytes)) return 1;
+    if (stage_out && ensure_pinned(&d.h_out, &d.h_out_cap, out_bytes)) return 1;
+    uint8_t *h_sigs = d.h_in, *h_msgs = d.h_in + n * 64, *h_pks = d.h_in + n * 96;
+    uint8_t *h_o = d.h_out, *h_st = d.h_out + n * 64;
+    Counter in_done[kMaxChunks], out_done;
+    struct WaitAll {  // no copy job may outlive this frame (they reference the caller's buffers and the counters)
+        Counter *a, *b;
+        ~WaitAll() {
+            for (int i = 0; i < kMaxChunks; i++) a[i].wait();
+            b->wait();
+        }
+    } wait_all{in_done, &out_done};
+    if (stage_in) {
+        size_t bounds[kMaxChunks + 1];
+        const int chunks = plan_pieces(d, n, bounds);
+        for (int c = 0; c < chunks; c++) {  // FIFO: piece 0 is staged first
+            const size_t lo = bounds[c], m = bounds[c + 1] - lo;
+            d.post_copy(h_sigs + lo * 64, sigs + lo * 64, m * 64, &in_done[c]);
+            d.post_copy(h_msgs + lo * 32, msgs + lo * 32, m * 32, &in_done[c]);
+            if (op == OP_ED) d.post_copy(h_pks + lo * 32, pks + lo * 32, m * 32, &in_done[c]);
+        }
+    }
+    auto up = [&](int c, size_t lo, size_t m, cudaStream_t st) -> int {
+        const uint8_t *s = sigs, *g = msgs, *k = pks;
+        if (stage_in) {
+            in_done[c].wait();
+            s = h_sigs;
+            g = h_msgs;
+            k = h_pks;
+        }
+        CK(cudaMemcpyAsync(d_sigs + lo * 64, s + lo * 64, m * 64, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_msgs + lo * 32, g + lo * 32, m * 32, cudaMemcpyHostToDevice, st));
+        if (op == OP_ED) CK(cudaMemcpyAsync(d_pks + lo * 32, k + lo * 32, m * 32, cudaMemcpyHostToDevice, st));
         return 0;
     };
-    auto launch = [&](size_t lo, size_t m, cudaStream_t st) -> int {
+    auto launch = [&](int, size_t lo, size_t m, cudaStream_t st) -> int {
         return launch_op(d, op, d_sigs + lo * 64, d_msgs + lo * 32, d_pks + lo * 32, m, d.d_out + lo * out_stride,
                          d_status ? d_status + lo : nullptr, st);
     };
-    auto down = [&](size_t lo, size_t m, cudaStream_t st) -> int {
-        CK(cudaMemcpyAsync(out + lo * out_stride, d.d_out + lo * out_stride, m * out_stride, cudaMemcpyDeviceToHost, st));
-        if (op != OP_ED && status) CK(cudaMemcpyAsync(status + lo, d_status + lo, m, cudaMemcpyDeviceToHost, st));
+    auto down = [&](int, size_t lo, size_t m, cudaStream_t st) -> int {
+        uint8_t* o = stage_out ? h_o : out;
+        uint8_t* s = stage_out ? h_st : status;
+        CK(cudaMemcpyAsync(o + lo * out_stride, d.d_out + lo * out_stride, m * out_stride, cudaMemcpyDeviceToHost, st));
+        if (op != OP_ED && status) CK(cudaMemcpyAsync(s + lo, d_status + lo, m, cudaMemcpyDeviceToHost, st));
         return 0;
     };
-    return run_pipeline(d, n, up, launch, down);
+    auto post = [&](int, size_t lo, size_t m) -> int {
+        d.post_copy(out + lo * out_stride, h_o + lo * out_stride, m * out_stride, &out_done);
+        if (op != OP_ED && status) d.post_copy(status + lo, h_st + lo, m, &out_done);
+        return 0;
+    };
+    const int rc = run_pipeline(d, n, inject_fail, stage_out, up, launch, down, post);
+    out_done.wait();
+    return rc;
 }
 
 // A device's shard is processed in sub-shards of at most kMaxSubShard signatures so that the device buffers stay
-// bounded (2 GiB in, 1 GiB out) however large the batch (the reference allows up to 2^30 signatures per call,
-// src/secp256k1_ecdsa.rs:22).  Timings accumulate over the sub-shards.
+// bounded (2 GiB in, 1 GiB out; the pinned staging of the pageable path is bounded the same way) however large the batch
+// (the reference allows up to 2^30 signatures per call, src/secp256k1_ecdsa.rs:22).  Timings accumulate over the sub-shards.
 constexpr size_t kMaxSubShard = (size_t)1 << 24;
+constexpr size_t kMaxSubShardStaged = (size_t)1 << 22;  // 512 MiB + 260 MiB of pinned staging per device at most
 
 int run_shard_bounded(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n,
-                      uint8_t* out, uint8_t* status) {
+                      uint8_t* out, uint8_t* status, bool inject_fail) {
     const size_t out_stride = op == OP_ED ? 1 : 64;
     float h2d = 0, ker = 0, d2h = 0;
     size_t sub = kMaxSubShard;
+    if (n > kMaxSubShardStaged && env_int("SIGOPS_STAGING", -1) != 0 && (is_pageable(sigs) || is_pageable(out)))
+        sub = kMaxSubShardStaged;
     if (const char* e = getenv("SIGOPS_MAX_SUBSHARD")) sub = std::max<size_t>(1, (size_t)atoll(e));  // test hook
     for (size_t lo = 0; lo < n; lo += sub) {
         const size_t m = std::min(sub, n - lo);
         if (int rc = run_shard(d, op, sigs + lo * 64, msgs + lo * 32, pks ? pks + lo * 32 : nullptr, m,
-                               out + lo * out_stride, status ? status + lo : nullptr))
+                               out + lo * out_stride, status ? status + lo : nullptr, inject_fail))
             return rc;
         h2d += d.ms_h2d;
         ker += d.ms_kernel;
@@ -407,44 +714,102 @@ int plan_shards(size_t n, int n_devices, size_t* bounds) {
     return (int)G;
 }
 
+// Runs fn(device, g, lo, hi) for every shard of an n-item batch: shard 0 on the calling thread, the others on their devices'
+// persistent workers; every shard holds its device's mutex while it runs.  `cand` (pool indices, may be empty = all) limits
+// the devices; when fewer devices than candidates are needed the idle ones are preferred.  One failed shard fails the whole
+// call (all-or-nothing, like ShaderFailureError).  Caller holds the pool lock (shared).
+template <class Fn>
+int for_each_shard(size_t n, const std::vector<int>& cand_in, Fn fn) {
+    auto& P = pool();
+    std::vector<int> cand = cand_in;
+    if (cand.empty())
+        for (size_t i = 0; i < P.size(); i++) cand.push_back((int)i);
+    std::vector<size_t> bounds(cand.size() + 1);
+    const size_t G = (size_t)plan_shards(n, (int)cand.size(), bounds.data());
+    std::vector<int> use;
+    if (G < cand.size()) {
+        for (int i : cand)
+            if (use.size() < G && P[i]->inflight.load() == 0) use.push_back(i);
+        for (int i : cand)
+            if (use.size() < G && std::find(use.begin(), use.end(), i) == use.end()) use.push_back(i);
+        std::sort(use.begin(), use.end());
+    } else {
+        use = cand;
+    }
+    const uint64_t call = ++g_call_seq;
+    t_last_call = call;
+    const int fail_dev = env_int("SIGOPS_FAIL_DEVICE", -1);
+    std::vector<int> rcs(G, 0);
+    Counter done;
+    auto shard = [&](size_t g) {
+        Device& d = *P[use[g]];
+        d.inflight++;
+        {
+            std::lock_guard<std::mutex> lk(d.mu);
+            d.ms_h2d = d.ms_kernel = d.ms_d2h = 0;
+            d.last_call = call;
+            rcs[g] = fn(d, bounds[g], bounds[g + 1], d.index == fail_dev);
+        }
+        d.inflight--;
+    };
+    if (G > 1) {
+        done.add(G - 1);
+        for (size_t g = 1; g < G; g++)
+            P[use[g]]->post([&, g] {
+                shard(g);
+                done.done();
+            });
+    }
+    shard(0);
+    done.wait();
+    for (size_t g = 0; g < G; g++)
+        if (rcs[g]) return rcs[g];
+    return 0;
+}
+
 int run_batch(Op op, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n, uint8_t* out,
-              uint8_t* status) {
-    std::lock_guard<std::mutex> lk(g_mu);
+              uint8_t* status, const int* dev_idx = nullptr, int n_idx = 0) {
     if (n == 0) return 0;
     if (!sigs || !msgs || !out || (op == OP_ED && !pks)) {
         set_err("null buffer");
         return 1;
     }
-    if (int rc = do_init(nullptr, 0)) return rc;
-    for (auto& d : g_dev) d.ms_h2d = d.ms_kernel = d.ms_d2h = 0;
-    std::vector<size_t> bounds(g_dev.size() + 1);
-    const size_t G = (size_t)plan_shards(n, (int)g_dev.size(), bounds.data());
-    const size_t out_stride = op == OP_ED ? 1 : 64;
-    if (G == 1) return run_shard_bounded(g_dev[0], op, sigs, msgs, pks, n, out, status);
-    std::vector<int> rcs(G, 0);
-    std::vector<std::thread> th;
-    for (size_t g = 0; g < G; g++) {
-        const size_t lo = bounds[g], hi = bounds[g + 1];  // contiguous shard [lo, hi)
-        th.emplace_back([&, g, lo, hi]() {
-            rcs[g] = run_shard_bounded(g_dev[g], op, sigs + lo * 64, msgs + lo * 32, pks ? pks + lo * 32 : nullptr, hi - lo,
-                               out + lo * out_stride, status ? status + lo : nullptr);
-        });
+    if (int rc = ensure_init()) return rc;
+    std::shared_lock<std::shared_mutex> lk(g_pool_mu);
+    if (!g_inited.load()) {
+        set_err("the device pool was shut down during the call");
+        return 1;
     }
-    for (auto& t : th) t.join();
-    for (size_t g = 0; g < G; g++)
-        if (rcs[g]) return rcs[g];  // one failed shard fails the whole call (all-or-nothing, like ShaderFailureError)
-    return 0;
+    std::vector<int> cand;
+    for (int i = 0; i < n_idx; i++) {
+        if (dev_idx[i] < 0 || dev_idx[i] >= (int)pool().size() || std::find(cand.begin(), cand.end(), dev_idx[i]) != cand.end()) {
+            set_err("device index out of range or repeated (indices refer to the pool, see sigops_num_devices)");
+            return 1;
+        }
+        cand.push_back(dev_idx[i]);
+    }
+    const size_t out_stride = op == OP_ED ? 1 : 64;
+    const int rc = for_each_shard(n, cand, [&](Device& d, size_t lo, size_t hi, bool inject_fail) {
+        return run_shard_bounded(d, op, sigs + lo * 64, msgs + lo * 32, pks ? pks + lo * 32 : nullptr, hi - lo,
+                                 out + lo * out_stride, status ? status + lo : nullptr, inject_fail);
+    });
+    if (rc) {  // all-or-nothing: no partial results are left behind
+        memset(out, 0, n * out_stride);
+        if (status) memset(status, op == OP_ED ? 0 : SIGOPS_STATUS_INVALID, n);
+    }
+    return rc;
 }
 
 int run_device(Op op, const void* d_sigs, const void* d_msgs, const void* d_pks, size_t n, void* d_out, void* d_status,
                void* stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (int rc = do_init(nullptr, 0)) return rc;
+    if (int rc = ensure_init()) return rc;
+    std::shared_lock<std::shared_mutex> lk(g_pool_mu);
     Device* d = current_device();
     if (!d) {
         set_err("current CUDA device is not part of the sigops pool");
         return 1;
     }
+    std::lock_guard<std::mutex> dl(d->mu);
     return launch_op(*d, op, (const uint8_t*)d_sigs, (const uint8_t*)d_msgs, (const uint8_t*)d_pks, n, (uint8_t*)d_out,
                      (uint8_t*)d_status, (cudaStream_t)stream);
 }
@@ -504,14 +869,17 @@ void sw_bases(std::vector<uint32_t>& out, const u32* gxy_table_entry0, const u32
 }
 
 
+
 // ---- streaming service mode -----------------------------------------------------------------------
-// A queue is a ring of `depth` slots on ONE device for ONE operation.  Every slot owns pinned host staging (inputs and
-// outputs), device buffers, its own per-thread scratch and its own stream, so the slots of a queue run concurrently on the
-// device: a request of a few thousand signatures occupies one or two warps per SM (launch_geometry), and up to 16 warps per
-// SM are resident, so `depth` small requests in flight multiply the throughput at the latency of one.  A slot's H2D copies,
-// kernel and D2H copies are replayed as one CUDA graph while the request size repeats (re-captured when it changes).
+// A queue is a ring of `depth` slots for ONE operation, on one device of the pool or spread round-robin over all of them
+// (device_index = -1).  Every slot owns pinned host staging (inputs and outputs), device buffers, its own per-thread
+// scratch and its own stream, so the slots of a queue run concurrently on the device: a request of a few thousand
+// signatures occupies one or two warps per SM (launch_geometry), and up to 16 warps per SM are resident, so `depth` small
+// requests in flight multiply the throughput at the latency of one.  A slot's H2D copies, kernel and D2H copies are
+// replayed as one CUDA graph while the request size repeats (re-captured when it changes).
 // Replaces the per-call device creation / buffer allocation / blocking poll of src/gpu.rs:5-35,129-170.
 struct QSlot {
+    Device* dev = nullptr;
     cudaStream_t st = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     uint8_t *h_in = nullptr, *h_out = nullptr;  // pinned: sigs (cap*64) | msgs (cap*32) | pks (cap*32); out (cap*64) | status (cap)
@@ -520,6 +888,7 @@ struct QSlot {
     cudaGraphExec_t exec = nullptr;
     size_t exec_n = 0;
     bool busy = false;
+    bool waiting = false;  // a thread is blocked in sigops_queue_wait on this slot
     size_t n = 0;
     float last_ms = 0;
 };
@@ -528,7 +897,7 @@ struct QSlot {
 
 struct sigops_queue {
     std::mutex mu;
-    Device* dev = nullptr;
+    int device_index = 0;  // -1: slots spread over the pool
     Op op = OP_K1;
     size_t cap = 0;
     bool graphs = true;
@@ -542,22 +911,30 @@ std::atomic<int> g_live_queues{0};
 
 inline size_t q_out_stride(Op op) { return op == OP_ED ? 1 : 64; }
 
-// enqueue one request of n signatures of slot s on stream st (also used under stream capture: no allocation, no sync)
-int queue_enqueue(sigops_queue* q, QSlot& s, size_t n, cudaStream_t st) {
+// enqueue the kernel and the downloads of one request of n signatures of slot s on stream st
+int queue_enqueue_tail(sigops_queue* q, QSlot& s, size_t n, cudaStream_t st) {
     const size_t cap = q->cap;
     const Op op = q->op;
-    CK(cudaMemcpyAsync(s.d_in, s.h_in, n * 64, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s.d_in + cap * 64, s.h_in + cap * 64, n * 32, cudaMemcpyHostToDevice, st));
-    if (op == OP_ED) CK(cudaMemcpyAsync(s.d_in + cap * 96, s.h_in + cap * 96, n * 32, cudaMemcpyHostToDevice, st));
     uint8_t* d_status = op == OP_ED ? nullptr : s.d_out + cap * 64;
-    if (launch_op_scratch(*q->dev, op, s.d_in, s.d_in + cap * 64, s.d_in + cap * 96, n, s.d_out, d_status, s.scratch, st))
+    if (launch_op_scratch(*s.dev, op, s.d_in, s.d_in + cap * 64, s.d_in + cap * 96, n, s.d_out, d_status, s.scratch, st))
         return 1;
     CK(cudaMemcpyAsync(s.h_out, s.d_out, n * q_out_stride(op), cudaMemcpyDeviceToHost, st));
     if (d_status) CK(cudaMemcpyAsync(s.h_out + cap * 64, d_status, n, cudaMemcpyDeviceToHost, st));
     return 0;
 }
 
+// the whole request: uploads from the slot's pinned arrays, kernel, downloads (also used under stream capture: no
+// allocation, no synchronisation)
+int queue_enqueue(sigops_queue* q, QSlot& s, size_t n, cudaStream_t st) {
+    const size_t cap = q->cap;
+    CK(cudaMemcpyAsync(s.d_in, s.h_in, n * 64, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.d_in + cap * 64, s.h_in + cap * 64, n * 32, cudaMemcpyHostToDevice, st));
+    if (q->op == OP_ED) CK(cudaMemcpyAsync(s.d_in + cap * 96, s.h_in + cap * 96, n * 32, cudaMemcpyHostToDevice, st));
+    return queue_enqueue_tail(q, s, n, st);
+}
+
 void queue_free_slot(QSlot& s) {
+    if (s.dev) cudaSetDevice(s.dev->id);
     if (s.exec) cudaGraphExecDestroy(s.exec);
     if (s.st) cudaStreamDestroy(s.st);
     if (s.t0) cudaEventDestroy(s.t0);
@@ -571,12 +948,13 @@ void queue_free_slot(QSlot& s) {
 }
 
 int queue_alloc_slot(sigops_queue* q, QSlot& s) {
-    const Device& d = *q->dev;
+    const Device& d = *s.dev;
     const size_t cap = q->cap;
     const int max_g = q->op == OP_K1 ? d.grid_k1 : q->op == OP_R1 ? d.grid_r1 : d.grid_ed;
     const size_t chunks = q->op == OP_ED ? kEdBatchChunks : kSwBatchChunks;
     // launch_geometry never uses more than min(max_g * 512, n + 512) threads for n signatures
     const size_t threads = std::min((size_t)max_g * kBlock, cap + (size_t)kBlock);
+    CK(cudaSetDevice(d.id));
     CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&s.t0));
     CK(cudaEventCreate(&s.t1));
@@ -588,48 +966,50 @@ int queue_alloc_slot(sigops_queue* q, QSlot& s) {
     return 0;
 }
 
+// shared head of the two submit calls: slot checks; returns the slot or nullptr
+QSlot* queue_submit_check(sigops_queue* q, int slot, size_t n, const char* who) {
+    if (!q || slot < 0 || slot >= (int)q->slots.size()) {
+        set_err(std::string(who) + ": bad queue or slot");
+        return nullptr;
+    }
+    QSlot& s = q->slots[slot];
+    if (s.busy) {
+        set_err(std::string(who) + ": slot is in flight (wait for it first)");
+        return nullptr;
+    }
+    if (n > q->cap) {
+        set_err(std::string(who) + ": n exceeds the queue's max_batch");
+        return nullptr;
+    }
+    return &s;
+}
+
 }  // namespace
 
 extern "C" {
 
 int sigops_init(const int* device_ids, int n_devices) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    return do_init(device_ids, n_devices);
+    std::unique_lock<std::shared_mutex> lk(g_pool_mu);
+    return do_init_locked(device_ids, n_devices);
 }
 
 int sigops_shutdown(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::unique_lock<std::shared_mutex> lk(g_pool_mu);
     if (g_live_queues.load() > 0) {
         set_err("sigops_shutdown: destroy every sigops_queue first");
         return 1;
     }
-    for (auto& d : g_dev) {
-        cudaSetDevice(d.id);
-        if (d.d_in) cudaFree(d.d_in);
-        if (d.d_out) cudaFree(d.d_out);
-        if (d.scratch) cudaFree(d.scratch);
-        if (d.k1g) cudaFree((void*)d.k1g);
-        if (d.r1g) cudaFree((void*)d.r1g);
-        if (d.edb) cudaFree((void*)d.edb);
-        for (auto& e : d.ev)
-            if (e) cudaEventDestroy(e);
-        for (auto& e : d.ev_in)
-            if (e) cudaEventDestroy(e);
-        for (auto& e : d.ev_k)
-            if (e) cudaEventDestroy(e);
-        if (d.stream) cudaStreamDestroy(d.stream);
-        if (d.s_in) cudaStreamDestroy(d.s_in);
-        if (d.s_out) cudaStreamDestroy(d.s_out);
-    }
-    g_dev.clear();
-    g_inited = false;
+    for (auto& d : pool()) free_device(*d);
+    pool().clear();
+    g_ids.clear();
+    g_inited.store(false);
     return 0;
 }
 
 int sigops_num_devices(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (do_init(nullptr, 0)) return 0;
-    return (int)g_dev.size();
+    if (ensure_init()) return 0;
+    std::shared_lock<std::shared_mutex> lk(g_pool_mu);
+    return (int)pool().size();
 }
 
 const char* sigops_last_error(void) {
@@ -655,10 +1035,20 @@ int sigops_ed25519_ecverify(const uint8_t* sigs, const uint8_t* msgs, const uint
     return run_batch(OP_ED, sigs, msgs, pks, n, out_valid, nullptr);
 }
 
+int sigops_batch_on_devices(int curve, const int* device_indices, int n_devices, const uint8_t* sigs, const uint8_t* msgs,
+                            const uint8_t* pks, size_t n, uint8_t* out, uint8_t* out_status) {
+    if (curve < SIGOPS_CURVE_SECP256K1 || curve > SIGOPS_CURVE_ED25519 || n_devices < 0 || (n_devices > 0 && !device_indices)) {
+        set_err("sigops_batch_on_devices: bad arguments");
+        return 1;
+    }
+    return run_batch((Op)curve, sigs, msgs, pks, n, out, curve == SIGOPS_CURVE_ED25519 ? nullptr : out_status, device_indices,
+                     n_devices);
+}
+
 // Variable-length-message ed25519: one device shard = signatures [lo, hi) and the message bytes they span, through the same
 // piecewise upload / kernel / download pipeline as the fixed-size entry points.
 static int run_ed_msgs_shard(Device& d, const uint8_t* sigs, const uint8_t* msg_bytes, const uint64_t* off, const uint8_t* pks,
-                             size_t n, uint32_t flags, uint8_t* out) {
+                             size_t n, uint32_t flags, uint8_t* out, bool inject_fail) {
     CK(cudaSetDevice(d.id));
     const uint64_t b0 = off[0], nbytes = off[n] - off[0];
     // layout: sigs | pks | offsets (n+1, rebased to 0) | message bytes
@@ -681,72 +1071,63 @@ static int run_ed_msgs_shard(Device& d, const uint8_t* sigs, const uint8_t* msg_
     }
     // the offsets go up first, in one piece (8 bytes per signature); `rebased` stays alive until the pipeline has drained
     CK(cudaMemcpyAsync(d_off, rebased.data(), off_bytes, cudaMemcpyHostToDevice, d.s_in));
-    auto up = [&](size_t lo, size_t m, cudaStream_t st) -> int {
+    auto up = [&](int, size_t lo, size_t m, cudaStream_t st) -> int {
         CK(cudaMemcpyAsync(d_sigs + lo * 64, sigs + lo * 64, m * 64, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(d_pks + lo * 32, pks + lo * 32, m * 32, cudaMemcpyHostToDevice, st));
         const uint64_t bl = rebased[lo], bh = rebased[lo + m];
         if (bh > bl) CK(cudaMemcpyAsync(d_msg + bl, msg_bytes + b0 + bl, (size_t)(bh - bl), cudaMemcpyHostToDevice, st));
         return 0;
     };
-    auto launch = [&](size_t lo, size_t m, cudaStream_t st) -> int {
-        int tpb = kBlock;
+    auto launch = [&](int, size_t lo, size_t m, cudaStream_t st) -> int {
+        KLaunch l;
+        l.stream = st;
+        l.tpb = kBlock;
         if (m < (size_t)d.sms * kBlock) {
             size_t per_sm = (m + d.sms - 1) / d.sms;
-            tpb = (int)std::min<size_t>(kBlock, std::max<size_t>(32, (per_sm + 31) / 32 * 32));
+            l.tpb = (int)std::min<size_t>(kBlock, std::max<size_t>(32, (per_sm + 31) / 32 * 32));
         }
-        int grid = (int)std::min<size_t>((m + tpb - 1) / tpb, (size_t)d.grid_edm);
-        ed25519_verify_msgs_kernel<<<grid, tpb, 0, st>>>((const Q4*)(d_sigs + lo * 64), d_msg,
-                                                         (const unsigned long long*)d_off + lo, (const Q4*)(d_pks + lo * 32), m,
-                                                         (int)(flags & SIGOPS_ED25519_STRICT), d.d_out + lo, d.scratch, d.edb);
-        CK(cudaGetLastError());
+        l.grid = (int)std::min<size_t>((m + l.tpb - 1) / l.tpb, (size_t)d.grid_edm);
+        if (d.scratch_used) CK(cudaStreamWaitEvent(st, d.scratch_ev, 0));
+        CK(kl_ed_verify_msgs(l, d_sigs + lo * 64, d_msg, (const unsigned long long*)d_off + lo, d_pks + lo * 32, m,
+                             (int)(flags & SIGOPS_ED25519_STRICT), d.d_out + lo, d.scratch, d.edb));
+        CK(cudaEventRecord(d.scratch_ev, st));
+        d.scratch_used = true;
         g_launches++;
         return 0;
     };
-    auto down = [&](size_t lo, size_t m, cudaStream_t st) -> int {
+    auto down = [&](int, size_t lo, size_t m, cudaStream_t st) -> int {
         CK(cudaMemcpyAsync(out + lo, d.d_out + lo, m, cudaMemcpyDeviceToHost, st));
         return 0;
     };
-    return run_pipeline(d, n, up, launch, down);
+    return run_pipeline(d, n, inject_fail, up, launch, down);
 }
 
 int sigops_ed25519_ecverify_msgs(const uint8_t* sigs, const uint8_t* msg_bytes, const uint64_t* msg_offsets,
                                  const uint8_t* pks, size_t n, uint32_t flags, uint8_t* out_valid) {
-    std::lock_guard<std::mutex> lk(g_mu);
     if (n == 0) return 0;
     if (!sigs || !msg_offsets || !pks || !out_valid || (!msg_bytes && msg_offsets[n] != msg_offsets[0])) {
         set_err("null buffer");
         return 1;
     }
-    if (int rc = do_init(nullptr, 0)) return rc;
-    for (auto& d : g_dev) d.ms_h2d = d.ms_kernel = d.ms_d2h = 0;
-    std::vector<size_t> bounds(g_dev.size() + 1);
-    const size_t G = (size_t)plan_shards(n, (int)g_dev.size(), bounds.data());
-    std::vector<int> rcs(G, 0);
-    std::vector<std::thread> th;
-    for (size_t g = 0; g < G; g++) {
-        const size_t lo = bounds[g], hi = bounds[g + 1];
-        auto work = [&, g, lo, hi]() {
-            // sub-shards bound the device buffers as in run_shard_bounded
-            for (size_t a = lo; a < hi && !rcs[g]; a += kMaxSubShard) {
-                const size_t m = std::min(kMaxSubShard, hi - a);
-                rcs[g] = run_ed_msgs_shard(g_dev[g], sigs + a * 64, msg_bytes, msg_offsets + a, pks + a * 32, m, flags,
-                                           out_valid + a);
-            }
-        };
-        if (G == 1)
-            work();
-        else
-            th.emplace_back(work);
-    }
-    for (auto& t : th) t.join();
-    for (size_t g = 0; g < G; g++)
-        if (rcs[g]) return rcs[g];
-    return 0;
+    if (int rc = ensure_init()) return rc;
+    std::shared_lock<std::shared_mutex> lk(g_pool_mu);
+    const int rc = for_each_shard(n, {}, [&](Device& d, size_t lo, size_t hi, bool inject_fail) {
+        // sub-shards bound the device buffers as in run_shard_bounded
+        for (size_t a = lo; a < hi; a += kMaxSubShard) {
+            const size_t m = std::min(kMaxSubShard, hi - a);
+            if (int r = run_ed_msgs_shard(d, sigs + a * 64, msg_bytes, msg_offsets + a, pks + a * 32, m, flags, out_valid + a,
+                                          inject_fail))
+                return r;
+        }
+        return 0;
+    });
+    if (rc) memset(out_valid, 0, n);
+    return rc;
 }
 
 // raw messages -> SHA-256 -> recover -> SHA-256(pubkey), all on the device, piece by piece; no host pass in between
 static int run_addresses_shard(Device& d, Op op, const uint8_t* sigs, const uint8_t* msg_bytes, const uint64_t* off, size_t n,
-                               uint8_t* out_addr, uint8_t* out_pk, uint8_t* out_st) {
+                               uint8_t* out_addr, uint8_t* out_pk, uint8_t* out_st, bool inject_fail) {
     CK(cudaSetDevice(d.id));
     const uint64_t b0 = off ? off[0] : 0, nbytes = off ? off[n] - off[0] : 0;
     const size_t off_bytes = off ? (n + 1) * sizeof(uint64_t) : 0;
@@ -772,7 +1153,7 @@ static int run_addresses_shard(Device& d, Op op, const uint8_t* sigs, const uint
         }
         CK(cudaMemcpyAsync(d_off, rebased.data(), off_bytes, cudaMemcpyHostToDevice, d.s_in));
     }
-    auto up = [&](size_t lo, size_t m, cudaStream_t st) -> int {
+    auto up = [&](int, size_t lo, size_t m, cudaStream_t st) -> int {
         CK(cudaMemcpyAsync(d_sigs + lo * 64, sigs + lo * 64, m * 64, cudaMemcpyHostToDevice, st));
         if (off) {
             const uint64_t bl = rebased[lo], bh = rebased[lo + m];
@@ -782,32 +1163,27 @@ static int run_addresses_shard(Device& d, Op op, const uint8_t* sigs, const uint
         }
         return 0;
     };
-    auto launch = [&](size_t lo, size_t m, cudaStream_t st) -> int {
+    auto launch = [&](int, size_t lo, size_t m, cudaStream_t st) -> int {
         if (off) {
-            sha256_msgs_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(d_raw, (const unsigned long long*)d_off + lo, m,
-                                                                           (u32*)(d_msgs + lo * 32));
-            CK(cudaGetLastError());
+            CK(kl_sha256_msgs(st, d_raw, (const unsigned long long*)d_off + lo, m, (u32*)(d_msgs + lo * 32)));
             g_launches++;
         }
         if (launch_op(d, op, d_sigs + lo * 64, d_msgs + lo * 32, nullptr, m, d.d_out + lo * 64, d_status + lo, st)) return 1;
-        sha256_pubkeys_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>((const u32*)(d.d_out + lo * 64), d_status + lo, m,
-                                                                          (u32*)(d_addr + lo * 32));
-        CK(cudaGetLastError());
+        CK(kl_sha256_pubkeys(st, (const u32*)(d.d_out + lo * 64), d_status + lo, m, (u32*)(d_addr + lo * 32)));
         g_launches++;
         return 0;
     };
-    auto down = [&](size_t lo, size_t m, cudaStream_t st) -> int {
+    auto down = [&](int, size_t lo, size_t m, cudaStream_t st) -> int {
         CK(cudaMemcpyAsync(out_addr + lo * 32, d_addr + lo * 32, m * 32, cudaMemcpyDeviceToHost, st));
         if (out_pk) CK(cudaMemcpyAsync(out_pk + lo * 64, d.d_out + lo * 64, m * 64, cudaMemcpyDeviceToHost, st));
         if (out_st) CK(cudaMemcpyAsync(out_st + lo, d_status + lo, m, cudaMemcpyDeviceToHost, st));
         return 0;
     };
-    return run_pipeline(d, n, up, launch, down);
+    return run_pipeline(d, n, inject_fail, up, launch, down);
 }
 
 int sigops_ecrecover_addresses(int curve, const uint8_t* sigs, const uint8_t* msg_bytes, const uint64_t* msg_offsets,
                                size_t n, uint8_t* out_addresses, uint8_t* out_pubkeys, uint8_t* out_status) {
-    std::lock_guard<std::mutex> lk(g_mu);
     if (n == 0) return 0;
     if (curve != SIGOPS_CURVE_SECP256K1 && curve != SIGOPS_CURVE_SECP256R1) {
         set_err("sigops_ecrecover_addresses: curve must be secp256k1 or secp256r1");
@@ -817,43 +1193,38 @@ int sigops_ecrecover_addresses(int curve, const uint8_t* sigs, const uint8_t* ms
         set_err("null buffer");
         return 1;
     }
-    if (int rc = do_init(nullptr, 0)) return rc;
-    for (auto& d : g_dev) d.ms_h2d = d.ms_kernel = d.ms_d2h = 0;
+    if (int rc = ensure_init()) return rc;
+    std::shared_lock<std::shared_mutex> lk(g_pool_mu);
     const Op op = curve == SIGOPS_CURVE_SECP256K1 ? OP_K1 : OP_R1;
-    std::vector<size_t> bounds(g_dev.size() + 1);
-    const size_t G = (size_t)plan_shards(n, (int)g_dev.size(), bounds.data());
-    std::vector<int> rcs(G, 0);
-    std::vector<std::thread> th;
-    for (size_t g = 0; g < G; g++) {
-        const size_t lo = bounds[g], hi = bounds[g + 1];
-        auto work = [&, g, lo, hi]() {
-            for (size_t a = lo; a < hi && !rcs[g]; a += kMaxSubShard) {
-                const size_t m = std::min(kMaxSubShard, hi - a);
-                rcs[g] = run_addresses_shard(g_dev[g], op, sigs + a * 64, msg_offsets ? msg_bytes : msg_bytes + a * 32,
-                                             msg_offsets ? msg_offsets + a : nullptr, m, out_addresses + a * 32,
-                                             out_pubkeys ? out_pubkeys + a * 64 : nullptr, out_status ? out_status + a : nullptr);
-            }
-        };
-        if (G == 1)
-            work();
-        else
-            th.emplace_back(work);
+    const int rc = for_each_shard(n, {}, [&](Device& d, size_t lo, size_t hi, bool inject_fail) {
+        for (size_t a = lo; a < hi; a += kMaxSubShard) {
+            const size_t m = std::min(kMaxSubShard, hi - a);
+            if (int r = run_addresses_shard(d, op, sigs + a * 64, msg_offsets ? msg_bytes : msg_bytes + a * 32,
+                                            msg_offsets ? msg_offsets + a : nullptr, m, out_addresses + a * 32,
+                                            out_pubkeys ? out_pubkeys + a * 64 : nullptr, out_status ? out_status + a : nullptr,
+                                            inject_fail))
+                return r;
+        }
+        return 0;
+    });
+    if (rc) {
+        memset(out_addresses, 0, n * 32);
+        if (out_pubkeys) memset(out_pubkeys, 0, n * 64);
+        if (out_status) memset(out_status, SIGOPS_STATUS_INVALID, n);
     }
-    for (auto& t : th) t.join();
-    for (size_t g = 0; g < G; g++)
-        if (rcs[g]) return rcs[g];
-    return 0;
+    return rc;
 }
 
 int sigops_sha256_batch(const uint8_t* data, const uint64_t* offsets, size_t n, uint8_t* out) {
-    std::lock_guard<std::mutex> lk(g_mu);
     if (n == 0) return 0;
     if (!offsets || !out || (!data && offsets[n] != offsets[0])) {
         set_err("null buffer");
         return 1;
     }
-    if (int rc = do_init(nullptr, 0)) return rc;
-    Device& d = g_dev[0];
+    if (int rc = ensure_init()) return rc;
+    std::shared_lock<std::shared_mutex> lk(g_pool_mu);
+    Device& d = *pool()[0];
+    std::lock_guard<std::mutex> dl(d.mu);
     CK(cudaSetDevice(d.id));
     for (size_t a = 0; a < n; a += kMaxSubShard) {
         const size_t m = std::min(kMaxSubShard, n - a);
@@ -869,14 +1240,22 @@ int sigops_sha256_batch(const uint8_t* data, const uint64_t* offsets, size_t n, 
             }
             rebased[i] = offsets[a + i] - b0;
         }
-        CK(cudaMemcpyAsync(d.d_in, rebased.data(), off_bytes, cudaMemcpyHostToDevice, d.stream));
-        if (nbytes) CK(cudaMemcpyAsync(d.d_in + off_bytes, data + b0, (size_t)nbytes, cudaMemcpyHostToDevice, d.stream));
-        sha256_msgs_kernel<<<(unsigned)((m + 255) / 256), 256, 0, d.stream>>>(d.d_in + off_bytes,
-                                                                             (const unsigned long long*)d.d_in, m, (u32*)d.d_out);
-        CK(cudaGetLastError());
-        g_launches++;
-        CK(cudaMemcpyAsync(out + a * 32, d.d_out, m * 32, cudaMemcpyDeviceToHost, d.stream));
-        CK(cudaStreamSynchronize(d.stream));
+        int rc = 0;
+        do {  // one pass; any failure drains the stream before `rebased` goes out of scope
+            rc = 1;
+            if (cudaMemcpyAsync(d.d_in, rebased.data(), off_bytes, cudaMemcpyHostToDevice, d.stream) != cudaSuccess) break;
+            if (nbytes && cudaMemcpyAsync(d.d_in + off_bytes, data + b0, (size_t)nbytes, cudaMemcpyHostToDevice, d.stream) != cudaSuccess) break;
+            if (kl_sha256_msgs(d.stream, d.d_in + off_bytes, (const unsigned long long*)d.d_in, m, (u32*)d.d_out)) break;
+            g_launches++;
+            if (cudaMemcpyAsync(out + a * 32, d.d_out, m * 32, cudaMemcpyDeviceToHost, d.stream) != cudaSuccess) break;
+            rc = 0;
+        } while (0);
+        cudaError_t e = cudaStreamSynchronize(d.stream);
+        if (rc || e != cudaSuccess) {
+            set_err(std::string("sigops_sha256_batch failed: ") + cudaGetErrorString(e != cudaSuccess ? e : cudaGetLastError()));
+            cudaGetLastError();
+            return 1;
+        }
     }
     return 0;
 }
@@ -904,9 +1283,12 @@ int sigops_plan_shards(size_t n, int n_devices, size_t* bounds, int* n_used) {
 }
 
 int sigops_last_timing(double* h2d_ms, double* kernel_ms, double* d2h_ms) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::shared_lock<std::shared_mutex> lk(g_pool_mu);
     double a = 0, b = 0, c = 0;
-    for (auto& d : g_dev) {
+    for (auto& dp : pool()) {
+        Device& d = *dp;
+        std::lock_guard<std::mutex> dl(d.mu);
+        if (d.last_call != t_last_call) continue;  // not part of the calling thread's last host-buffer call
         a = std::max(a, (double)d.ms_h2d);
         b = std::max(b, (double)d.ms_kernel);
         c = std::max(c, (double)d.ms_d2h);
@@ -996,14 +1378,15 @@ int sigops_test_unit_shape(int op, int* in_words, int* out_words) {
 }
 
 int sigops_test_unit(int op, const uint32_t* in, size_t n, uint32_t* out) {
-    std::lock_guard<std::mutex> lk(g_mu);
     if (op < 0 || op >= SIGOPS_UNIT_COUNT) {
         set_err("bad unit op");
         return 1;
     }
     if (n == 0) return 0;
-    if (int rc = do_init(nullptr, 0)) return rc;
-    Device& d = g_dev[0];
+    if (int rc = ensure_init()) return rc;
+    std::shared_lock<std::shared_mutex> lk(g_pool_mu);
+    Device& d = *pool()[0];
+    std::lock_guard<std::mutex> dl(d.mu);
     CK(cudaSetDevice(d.id));
     int in_w, out_w;
     unit_shape(op, in_w, out_w);
@@ -1011,9 +1394,14 @@ int sigops_test_unit(int op, const uint32_t* in, size_t n, uint32_t* out) {
     if (ensure_buf(&d.d_out, &d.out_cap, n * out_w * 4)) return 1;
     if (ensure_scratch(d, (size_t)kEdTabChunks * d.grid_unit * kBlock)) return 1;
     CK(cudaMemcpyAsync(d.d_in, in, n * in_w * 4, cudaMemcpyHostToDevice, d.stream));
-    int grid = (int)std::min<size_t>((n + kBlock - 1) / kBlock, (size_t)d.grid_unit);
-    unit_kernel<<<grid, kBlock, 0, d.stream>>>(op, (const u32*)d.d_in, n, (u32*)d.d_out, d.scratch, d.k1g, d.r1g, d.edb);
-    CK(cudaGetLastError());
+    KLaunch l;
+    l.stream = d.stream;
+    l.tpb = kBlock;
+    l.grid = (int)std::min<size_t>((n + kBlock - 1) / kBlock, (size_t)d.grid_unit);
+    if (d.scratch_used) CK(cudaStreamWaitEvent(d.stream, d.scratch_ev, 0));
+    CK(kl_unit(l, op, (const u32*)d.d_in, n, (u32*)d.d_out, d.scratch, d.k1g, d.r1g, d.edb));
+    CK(cudaEventRecord(d.scratch_ev, d.stream));
+    d.scratch_used = true;
     g_launches++;
     CK(cudaMemcpyAsync(out, d.d_out, n * out_w * 4, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaStreamSynchronize(d.stream));
@@ -1021,26 +1409,22 @@ int sigops_test_unit(int op, const uint32_t* in, size_t n, uint32_t* out) {
 }
 
 int sigops_imad_peak(int kind, int iters, double* ops_per_sec, double* ms_out) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (int rc = do_init(nullptr, 0)) return rc;
-    Device& d = g_dev[0];
+    if (int rc = ensure_init()) return rc;
+    std::shared_lock<std::shared_mutex> lk(g_pool_mu);
+    Device* dp = current_device();  // the pool device the caller is on, else the first one
+    Device& d = dp ? *dp : *pool()[0];
+    std::lock_guard<std::mutex> dl(d.mu);
     CK(cudaSetDevice(d.id));
     if (ensure_buf(&d.d_out, &d.out_cap, (size_t)d.sms * 8 * 256 * 4)) return 1;
     const int grid = d.sms * 8, block = 256;  // 2048 threads per SM: full occupancy
-    double per_thread_iter;
-    for (int rep = 0; rep < 2; rep++) {  // first pass warms up
+    for (int rep = 0; rep < 2; rep++) {       // first pass warms up
         CK(cudaEventRecord(d.ev[0], d.stream));
-        switch (kind) {
-            case 0: imad_peak_kernel<0><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
-            case 1: imad_peak_kernel<1><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
-            case 2: imad_peak_kernel<2><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
-            case 3: imad_peak_kernel<3><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
-            case 4: imad_peak_kernel<4><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
-            case 5: imad_peak_kernel<5><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
-            case 6: imad_peak_kernel<6><<<grid, block, 0, d.stream>>>((u32*)d.d_out, iters, 12345u); break;
-            default: set_err("bad kind"); return 1;
+        int rc = kl_imad_peak(kind, grid, block, d.stream, (u32*)d.d_out, iters, 12345u);
+        if (rc == -1) {
+            set_err("bad kind");
+            return 1;
         }
-        CK(cudaGetLastError());
+        CK(rc);
         CK(cudaEventRecord(d.ev[1], d.stream));
         CK(cudaStreamSynchronize(d.stream));
     }
@@ -1049,13 +1433,12 @@ int sigops_imad_peak(int kind, int iters, double* ops_per_sec, double* ms_out) {
     // counted operations per thread per outer iteration (16 unrolled blocks):
     //  kind 0: 8 IMAD; 1: 8 IMAD.WIDE; 2: 8 IMAD.WIDE(.X); 3: 8 IADD; 4: 8 IMAD.WIDE + 8 IADD (counted: the 8 wide);
     //  5: 8 DFMA; 6: 8 IMAD.HI
-    per_thread_iter = 16.0 * 8.0;
+    const double per_thread_iter = 16.0 * 8.0;
     double ops = per_thread_iter * (double)iters * (double)grid * block;
     if (ops_per_sec) *ops_per_sec = ops / (ms * 1e-3);
     if (ms_out) *ms_out = ms;
     return 0;
 }
-
 
 // ---- streaming service mode: C entry points ----------------------------------------------------------------------------
 int sigops_queue_create(int curve, int device_index, size_t max_batch, int depth, sigops_queue** out) {
@@ -1069,29 +1452,28 @@ int sigops_queue_create(int curve, int device_index, size_t max_batch, int depth
         set_err("sigops_queue_create: bad arguments (curve 0..2, 1 <= max_batch <= 2^24, 1 <= depth <= 64)");
         return 1;
     }
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (int rc = do_init(nullptr, 0)) return rc;
-    if (device_index < 0 || device_index >= (int)g_dev.size()) {
-        set_err("sigops_queue_create: device_index is not in the pool");
+    if (int rc = ensure_init()) return rc;
+    std::shared_lock<std::shared_mutex> lk(g_pool_mu);
+    auto& P = pool();
+    if (device_index < -1 || device_index >= (int)P.size()) {
+        set_err("sigops_queue_create: device_index is not in the pool (-1 = spread the slots over all devices)");
         return 1;
     }
     sigops_queue* q = new sigops_queue();
-    q->dev = &g_dev[device_index];
+    q->device_index = device_index;
     q->op = (Op)curve;
     q->cap = max_batch;
     if (const char* e = getenv("SIGOPS_QUEUE_GRAPHS")) q->graphs = atoi(e) != 0;
     q->slots.resize(depth);
-    if (cudaSetDevice(q->dev->id) != cudaSuccess) {
-        set_err("sigops_queue_create: cudaSetDevice failed");
-        delete q;
-        return 1;
-    }
-    for (auto& s : q->slots)
+    for (int i = 0; i < depth; i++) {
+        QSlot& s = q->slots[i];
+        s.dev = P[device_index >= 0 ? device_index : i % (int)P.size()].get();
         if (queue_alloc_slot(q, s)) {
             for (auto& t : q->slots) queue_free_slot(t);
             delete q;
             return 1;
         }
+    }
     g_live_queues++;
     *out = q;
     return 0;
@@ -1101,8 +1483,8 @@ int sigops_queue_destroy(sigops_queue* q) {
     if (!q) return 0;
     {
         std::lock_guard<std::mutex> lk(q->mu);
-        cudaSetDevice(q->dev->id);
         for (auto& s : q->slots) {
+            if (s.dev) cudaSetDevice(s.dev->id);
             if (s.st) cudaStreamSynchronize(s.st);
             queue_free_slot(s);
         }
@@ -1128,24 +1510,18 @@ int sigops_queue_buffers(sigops_queue* q, int slot, uint8_t** sigs, uint8_t** ms
 }
 
 int sigops_queue_submit(sigops_queue* q, int slot, size_t n) {
-    if (!q || slot < 0 || slot >= (int)q->slots.size()) {
+    if (!q) {
         set_err("sigops_queue_submit: bad queue or slot");
         return 1;
     }
     std::lock_guard<std::mutex> lk(q->mu);
-    QSlot& s = q->slots[slot];
-    if (s.busy) {
-        set_err("sigops_queue_submit: slot is in flight (wait for it first)");
-        return 1;
-    }
-    if (n > q->cap) {
-        set_err("sigops_queue_submit: n exceeds the queue's max_batch");
-        return 1;
-    }
+    QSlot* sp = queue_submit_check(q, slot, n, "sigops_queue_submit");
+    if (!sp) return 1;
+    QSlot& s = *sp;
     s.n = n;
     s.last_ms = 0;
     if (n == 0) return 0;  // nothing to do: the slot stays free (src/secp256k1_ecdsa.rs:71-73)
-    CK(cudaSetDevice(q->dev->id));
+    CK(cudaSetDevice(s.dev->id));
     if (q->graphs && s.exec_n != n) {
         // (re)capture the slot's copy / kernel / copy sequence for this request size
         cudaGraph_t g = nullptr;
@@ -1157,6 +1533,7 @@ int sigops_queue_submit(sigops_queue* q, int slot, size_t n) {
         if (rc || e != cudaSuccess) {
             if (g) cudaGraphDestroy(g);
             if (!rc) set_err(std::string("cudaStreamEndCapture failed: ") + cudaGetErrorString(e));
+            cudaGetLastError();
             return 1;
         }
         bool updated = false;
@@ -1186,9 +1563,58 @@ int sigops_queue_submit(sigops_queue* q, int slot, size_t n) {
     CK(cudaEventRecord(s.t0, s.st));
     if (q->graphs) {
         CK(cudaGraphLaunch(s.exec, s.st));
-        g_launches += tail_split(*q->dev, n) < n ? 2 : 1;  // the fused kernel (twice when the tail is launched on its own)
+        g_launches += tail_split(*s.dev, n) < n ? 2 : 1;  // the fused kernel (twice when the tail is launched on its own)
         q->graph_launches++;
     } else if (queue_enqueue(q, s, n, s.st)) {
+        return 1;
+    }
+    CK(cudaEventRecord(s.t1, s.st));
+    s.busy = true;
+    return 0;
+}
+
+int sigops_queue_submit_device(sigops_queue* q, int slot, const void* d_sigs, const void* d_msgs, const void* d_pks, size_t n,
+                               int src_device, void* ready_event) {
+    if (!q) {
+        set_err("sigops_queue_submit_device: bad queue or slot");
+        return 1;
+    }
+    std::lock_guard<std::mutex> lk(q->mu);
+    QSlot* sp = queue_submit_check(q, slot, n, "sigops_queue_submit_device");
+    if (!sp) return 1;
+    QSlot& s = *sp;
+    if (!d_sigs || !d_msgs || (q->op == OP_ED && !d_pks)) {
+        set_err("sigops_queue_submit_device: null buffer");
+        return 1;
+    }
+    s.n = n;
+    s.last_ms = 0;
+    if (n == 0) return 0;
+    const int dst = s.dev->id;
+    CK(cudaSetDevice(dst));
+    if (src_device != dst) {  // direct NVLink path when the devices are peers; the copy still works (staged) when they are not
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, dst, src_device) == cudaSuccess && can) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(src_device, 0);
+            if (e != cudaSuccess) cudaGetLastError();  // already enabled
+        }
+    }
+    const size_t cap = q->cap;
+    if (ready_event) CK(cudaStreamWaitEvent(s.st, (cudaEvent_t)ready_event, 0));
+    CK(cudaEventRecord(s.t0, s.st));
+    int rc = 0;
+    do {
+        rc = 1;
+        if (cudaMemcpyPeerAsync(s.d_in, dst, d_sigs, src_device, n * 64, s.st) != cudaSuccess) break;
+        if (cudaMemcpyPeerAsync(s.d_in + cap * 64, dst, d_msgs, src_device, n * 32, s.st) != cudaSuccess) break;
+        if (q->op == OP_ED && cudaMemcpyPeerAsync(s.d_in + cap * 96, dst, d_pks, src_device, n * 32, s.st) != cudaSuccess) break;
+        rc = queue_enqueue_tail(q, s, n, s.st);
+    } while (0);
+    if (rc) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) set_err(std::string("sigops_queue_submit_device: ") + cudaGetErrorString(e));
+        cudaStreamSynchronize(s.st);  // nothing of the failed request stays in flight
+        cudaGetLastError();
         return 1;
     }
     CK(cudaEventRecord(s.t1, s.st));
@@ -1234,12 +1660,28 @@ int sigops_queue_wait(sigops_queue* q, int slot, size_t* n_done, double* device_
             if (device_ms) *device_ms = s.last_ms;
             return 0;
         }
+        if (s.waiting) {  // one waiter per slot: a second one would race on the slot's state
+            set_err("sigops_queue_wait: another thread is already waiting on this slot");
+            return 1;
+        }
+        s.waiting = true;
         ev = s.t1;
     }
-    CK(cudaEventSynchronize(ev));  // outside the queue lock: other threads keep submitting to other slots
+    const cudaError_t e = cudaEventSynchronize(ev);  // outside the queue lock: other threads keep submitting to other slots
     std::lock_guard<std::mutex> lk(q->mu);
-    CK(cudaEventElapsedTime(&s.last_ms, s.t0, s.t1));
+    // whatever happened, the slot is released: a failed request must not wedge the queue
+    s.waiting = false;
     s.busy = false;
+    s.last_ms = 0;
+    if (e != cudaSuccess) {
+        set_err(std::string("sigops_queue_wait: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+        return 1;
+    }
+    if (cudaEventElapsedTime(&s.last_ms, s.t0, s.t1) != cudaSuccess) {
+        cudaGetLastError();
+        s.last_ms = 0;
+    }
     if (n_done) *n_done = s.n;
     if (device_ms) *device_ms = s.last_ms;
     return 0;
@@ -1253,12 +1695,17 @@ int sigops_queue_info(sigops_queue* q, int* curve, int* device_index, size_t* ma
     }
     std::lock_guard<std::mutex> lk(q->mu);
     if (curve) *curve = (int)q->op;
-    if (device_index) *device_index = (int)(q->dev - g_dev.data());
+    if (device_index) *device_index = q->device_index;
     if (max_batch) *max_batch = q->cap;
     if (depth) *depth = (int)q->slots.size();
     if (graph_launches) *graph_launches = q->graph_launches;
     if (graph_captures) *graph_captures = q->graph_captures;
     return 0;
+}
+
+int sigops_queue_slot_device(sigops_queue* q, int slot) {
+    if (!q || slot < 0 || slot >= (int)q->slots.size()) return -1;
+    return q->slots[slot].dev->id;
 }
 
 }  // extern "C"

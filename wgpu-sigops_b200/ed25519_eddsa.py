@@ -30,7 +30,8 @@ def ecverify_msgs(signatures, messages: Sequence[bytes], verifying_keys, strict:
     sigs = _batch.flatten(signatures, 64, "signature")
     pks = _batch.flatten(verifying_keys, 32, "verifying key")
     n = sigs.shape[0]
-    assert n == pks.shape[0] == len(messages)
+    if not (n == pks.shape[0] == len(messages)):
+        raise _batch.LengthMismatch("signatures, messages and verifying keys differ in length")
     out = np.zeros(n, dtype=np.uint8)
     if n == 0:
         return out

@@ -41,11 +41,13 @@ def ecrecover_addresses(curve: str, signatures, messages, prehashed: bool = Fals
     lib = _lib.load()
     if prehashed:
         msgs = _batch.flatten(messages, 32, "message")
-        assert msgs.shape[0] == n
+        if msgs.shape[0] != n:
+            raise _batch.LengthMismatch("signatures and messages differ in length")
         _lib.check(lib.sigops_ecrecover_addresses(cid, sigs.ctypes.data, msgs.ctypes.data, None, n, addr.ctypes.data,
                                                   pks.ctypes.data, st.ctypes.data))
     else:
-        assert len(messages) == n
+        if len(messages) != n:
+            raise _batch.LengthMismatch("signatures and messages differ in length")
         blob, offs = _blob(messages)
         _lib.check(lib.sigops_ecrecover_addresses(cid, sigs.ctypes.data, blob.ctypes.data, offs.ctypes.data, n,
                                                   addr.ctypes.data, pks.ctypes.data, st.ctypes.data))

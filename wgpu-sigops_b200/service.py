@@ -10,7 +10,11 @@ small requests (they occupy only a fraction of each SM).
     slot = 0
     q.sigs(slot)[:n] = ...; q.msgs(slot)[:n] = ...        # write straight into pinned memory
     q.submit(slot, n)                                      # asynchronous
-    keys, status = q.wait(slot)                            # views of the slot's pinned output arrays (n rows)
+    keys, status = q.wait(slot)                            # copies of the slot's results (n rows)
+
+`device_index=-1` spreads the slots round-robin over every GPU of the pool.  `wait(slot, copy=False)` returns views of
+the slot's pinned output arrays instead of copies: valid only until the slot is submitted again or the queue is closed
+(close() frees the pinned memory -- the queue refuses to close while such views are handed out unless force=True).
 """
 import ctypes
 from typing import Optional, Tuple
@@ -38,6 +42,7 @@ class SigQueue:
         self._q = ctypes.c_void_p()
         _lib.check(self._lib.sigops_queue_create(self.cid, device_index, self.max_batch, self.depth, ctypes.byref(self._q)))
         self._bufs = []
+        self._views_out = 0
         for s in range(self.depth):
             p = [ctypes.c_void_p() for _ in range(5)]
             _lib.check(self._lib.sigops_queue_buffers(self._q, s, *[ctypes.byref(x) for x in p]))
@@ -66,15 +71,32 @@ class SigQueue:
         _lib.check(self._lib.sigops_queue_poll(self._q, slot, ctypes.byref(d)))
         return bool(d.value)
 
-    def wait(self, slot: int) -> Tuple[np.ndarray, Optional[np.ndarray]]:
-        """Blocks until the slot's request has completed.  Returns views (valid until the slot is submitted again):
-        (keys n x 64, status n) for the recovery curves, (verdicts n, None) for ed25519."""
+    def submit_device(self, slot: int, d_sigs: int, d_msgs: int, d_pks: Optional[int], n: int, src_device: int,
+                      ready_event: Optional[int] = None) -> None:
+        """Device-resident producer: the inputs are device pointers on CUDA device `src_device`; they reach the slot's
+        device with cudaMemcpyPeerAsync (NVLink between peers).  ready_event: a cudaEvent_t handle to wait for, or None."""
+        _lib.check(self._lib.sigops_queue_submit_device(self._q, slot, d_sigs, d_msgs, d_pks, n, src_device, ready_event))
+
+    def slot_device(self, slot: int) -> int:
+        """CUDA ordinal of the device the slot lives on."""
+        return self._lib.sigops_queue_slot_device(self._q, slot)
+
+    def wait(self, slot: int, copy: bool = True) -> Tuple[np.ndarray, Optional[np.ndarray]]:
+        """Blocks until the slot's request has completed.  Returns (keys n x 64, status n) for the recovery curves,
+        (verdicts n, None) for ed25519 -- copies by default; with copy=False views of the slot's pinned arrays, valid only
+        until the slot is submitted again or the queue is closed."""
+        if not self._q:
+            raise ValueError("queue is closed")
         n = ctypes.c_size_t(0)
         ms = ctypes.c_double(0)
         _lib.check(self._lib.sigops_queue_wait(self._q, slot, ctypes.byref(n), ctypes.byref(ms)))
         self.last_device_ms = ms.value
         out, st = self._bufs[slot][3], self._bufs[slot][4]
-        return out[: n.value], (st[: n.value] if st is not None else None)
+        out, st = out[: n.value], (st[: n.value] if st is not None else None)
+        if copy:
+            return out.copy(), (st.copy() if st is not None else None)
+        self._views_out += 1
+        return out, st
 
     def info(self) -> dict:
         c, d, dep = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
@@ -85,8 +107,13 @@ class SigQueue:
         return {"curve": c.value, "device_index": d.value, "max_batch": mb.value, "depth": dep.value,
                 "graph_launches": gl.value, "graph_captures": gc.value}
 
-    def close(self) -> None:
+    def close(self, force: bool = False) -> None:
+        """Destroys the queue and frees its pinned memory.  Views handed out by wait(copy=False) / sigs() / msgs() dangle
+        afterwards, so closing with views outstanding needs force=True (the context manager and __del__ force)."""
         if self._q:
+            if self._views_out and not force:
+                raise RuntimeError("SigQueue.close(): %d result view(s) were handed out with copy=False; they would point "
+                                   "at freed pinned memory -- drop them and pass force=True" % self._views_out)
             self._bufs = []
             self._lib.sigops_queue_destroy(self._q)
             self._q = ctypes.c_void_p()
@@ -95,11 +122,11 @@ class SigQueue:
         return self
 
     def __exit__(self, *a):
-        self.close()
+        self.close(force=True)
 
     def __del__(self):
         try:
-            self.close()
+            self.close(force=True)
         except Exception:
             pass
 
@@ -113,8 +140,7 @@ def run_stream(curve: str, requests, max_batch: int, depth: int = 4, device_inde
 
         def drain_one():
             slot = pending.pop(0)
-            out, st = q.wait(slot)
-            res = (out.copy(), st.copy() if st is not None else None)
+            res = q.wait(slot)
             free.append(slot)
             return res
 
