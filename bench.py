@@ -36,7 +36,7 @@ import time
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "oracle")):
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -45,10 +45,29 @@ import numpy as np  # noqa: E402
 BATCH = 1 << 20
 # algorithmic work per signature in IMAD-equivalents (2 x 32x32->64 limb-MACs)
 IMAD_EQ = {"secp256k1": 451_616, "secp256r1": 554_784, "ed25519": 461_400}
-# Wide MACs (IMAD.WIDE.U32[.X]) actually executed per signature, from the ncu source page of the committed capture
-# (profiles/r01_ncu_instruction_mix.txt); x2 = IMAD-equivalents.  Reported next to the contract figure so that a
-# contract-based fraction above 1.0 can be read against what the multiplier pipe really did.
-EXECUTED_WIDE_MACS = {"secp256k1": 133_229, "secp256r1": 165_708, "ed25519": 167_901}
+# Wide MACs (IMAD.WIDE.U32[.X]) actually executed per signature come from the ncu source page of a committed capture
+# (profiles/executed_macs.json, written by tools/ncu_mix.py --json and tagged with the hash of the library sources it was
+# taken from); x2 = IMAD-equivalents.  Reported next to the contract figure so that a contract-based fraction above 1.0
+# can be read against what the multiplier pipe really did.  A capture of different sources is refused (executed_frac null).
+
+
+def executed_wide_macs():
+    """-> (dict curve -> wide MACs per signature, or None; note)."""
+    path = os.path.join(ROOT, "profiles", "executed_macs.json")
+    if not os.path.exists(path):
+        return None, "profiles/executed_macs.json is missing"
+    rec = json.load(open(path))
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_sigops_build", os.path.join(ROOT, "wgpu-sigops_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    now = b.source_hash()
+    if rec.get("source_hash") != now:
+        return None, ("profiles/executed_macs.json was captured from library sources %s, the library is now %s: "
+                      "executed_frac withheld until the capture is redone" % (rec.get("source_hash"), now))
+    return rec["wide_macs_per_signature"], "ncu source page, %s, sources %s" % (rec.get("capture", "?"), now)
+
 # HBM bytes per signature (inputs + outputs incl. the status byte)
 HBM_BYTES = {"secp256k1": 96 + 65, "secp256r1": 96 + 65, "ed25519": 128 + 1}
 CURVES = ("secp256k1", "secp256r1", "ed25519")
@@ -182,6 +201,185 @@ def queue_throughput(w, curve: str, req_n: int, depth: int, n_requests: int, poo
             "graph_launches": info["graph_launches"], "graph_captures": info["graph_captures"]}
 
 
+
+# ------------------------------------------------------------------------------------------------ configs 4 and 5
+def _pinned_copy(lib, a):
+    ptr = lib.sigops_host_alloc(max(1, a.nbytes))
+    buf = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(max(1, a.nbytes),))
+    buf[: a.nbytes] = a.reshape(-1).view(np.uint8)
+    return ptr
+
+
+def _pinned_out(lib, nbytes):
+    ptr = lib.sigops_host_alloc(max(1, nbytes))
+    return ptr, np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(max(1, nbytes),))
+
+
+def _pct(xs, q):
+    xs = sorted(xs)
+    return xs[min(len(xs) - 1, int(len(xs) * q))]
+
+
+def single_process_legs(lib, G, args, threads):
+    """BASELINE config 4 literally -- one 1,048,576-signature secp256k1 block (0.1 % edge rows: high-s, r/s out of range,
+    x not on the curve, Q = infinity, z >= n, wrong parity ...) in ONE `sigops_secp256k1_ecrecover` call that the library
+    shards over all G devices of this process -- and config 5, the mixed k1 / r1 / ed25519 batch-size sweep (three
+    back-to-back calls of n/3 signatures each, p50 / p99 latency and aggregate throughput).  Mirrors the reference's
+    benchmark protocol (src/benchmarks/secp256k1_ecdsa.rs:10-55,102-147: size sweep, check = true): every output row of the
+    strong leg and of one repetition per sweep size is compared with the expected keys / status / verdicts.
+    Returns (strong, sweep, kernel launches)."""
+    import batches
+
+    ids = (ctypes.c_int * G)(*range(G))
+    if lib.sigops_init(ids, G) != 0:
+        raise SystemExit("sigops_init(all devices): " + lib.sigops_last_error().decode())
+    l0 = lib.sigops_kernel_launches()
+    n = args.batch
+    t_gen = time.time()
+    sigs, msgs, exp_pk, exp_st, n_edge = batches.ecdsa_batch(0, n, edge_every=1000, seed=0x51600004)
+    log(f"[strong] generated {n} secp256k1 signatures with {n_edge} edge rows ({int(exp_st.sum())} rejected) in {time.time() - t_gen:.1f}s")
+    p_s, p_m = _pinned_copy(lib, sigs), _pinned_copy(lib, msgs)
+    p_o, v_o = _pinned_out(lib, n * 64)
+    p_t, v_t = _pinned_out(lib, n)
+    reps = max(10, args.steps)
+
+    def timed(call, reps):
+        ts = []
+        for _ in range(reps):
+            v_o[:] = 0xAA
+            v_t[:] = 0xAA
+            t0 = time.perf_counter()
+            rc = call()
+            ts.append(time.perf_counter() - t0)
+            if rc != 0:
+                raise SystemExit("strong leg: call failed: " + lib.sigops_last_error().decode())
+            if not ((v_o.reshape(n, 64) == exp_pk).all() and (v_t == exp_st).all()):
+                raise SystemExit("strong leg: keys / status differ from the expected values -- refusing to report")
+        return ts
+
+    by_dev = {}
+    counts = sorted({g for g in (1, 2, 4, 8) if g < G} | {G})
+    for g in counts:
+        sub = (ctypes.c_int * g)(*range(g))
+        if g == G:
+            call = lambda: lib.sigops_secp256k1_ecrecover(p_s, p_m, n, p_o, p_t)  # noqa: E731  the drop-in call itself
+        else:
+            call = lambda sub=sub, g=g: lib.sigops_batch_on_devices(0, sub, g, p_s, p_m, None, n, p_o, p_t)  # noqa: E731
+        timed(call, 3)
+        ts = timed(call, reps if g in (1, G) else max(5, reps // 2))
+        by_dev[g] = {"ms_p50": _pct(ts, 0.5) * 1e3, "ms_p99": _pct(ts, 0.99) * 1e3, "ms_min": min(ts) * 1e3}
+    t1, tG = by_dev[1]["ms_p50"], by_dev[G]["ms_p50"]
+    for g in counts:
+        by_dev[g]["sigs_per_s"] = n / (by_dev[g]["ms_p50"] * 1e-3)
+        by_dev[g]["efficiency_vs_n1"] = t1 / (g * by_dev[g]["ms_p50"])
+    h2d, ker, d2h = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    lib.sigops_last_timing(ctypes.byref(h2d), ctypes.byref(ker), ctypes.byref(d2h))
+    strong = {"workload": "secp256k1 ecrecover, ONE 1,048,576-signature block, one sigops_secp256k1_ecrecover call, sharded "
+                          "in-process over the devices (BASELINE config 4)",
+              "n": n, "n_devices": G, "edge_rows": int(n_edge), "rejected_rows": int(exp_st.sum()),
+              "ms_p50": tG, "sigs_per_s": n / (tG * 1e-3), "efficiency_vs_n1": t1 / (G * tG), "reps": reps,
+              "by_devices": {str(g): v for g, v in by_dev.items()},
+              "last_call_ms": {"h2d": h2d.value, "kernel": ker.value, "d2h": d2h.value},
+              "host_buffers": "pinned", "timing": "host wall clock around the blocking call (H2D + kernels + D2H inside)",
+              "parity": "every repetition: all rows, keys and status, bit-exact vs the oracle-labelled batch"}
+    log("[strong] " + ", ".join(f"{g} GPU: {by_dev[g]['ms_p50']:.2f} ms (eff {by_dev[g]['efficiency_vs_n1']:.2f})" for g in counts))
+    for ptr in (p_s, p_m, p_o, p_t):
+        lib.sigops_host_free(ptr)
+
+    # ---- config 5: mixed sweep.  Pools of 349,526 rows per curve (k1 / r1 with 0.1 % edge rows, ed25519 with 1 % edge
+    #      classes); sizes above 1M tile the pool (pageable numpy arrays, the library's staged path) ----
+    pool_n = (1 << 20) // 3 + 1
+    pk1 = batches.ecdsa_batch(0, pool_n, edge_every=1000, seed=0x51600005)
+    pr1 = batches.ecdsa_batch(1, pool_n, edge_every=1000, seed=0x51600006, mix_high_s=True)
+    ped = batches.ed25519_batch(pool_n, edge_every=100, seed=0x51600007)
+    pin = {"k1": [_pinned_copy(lib, a) for a in pk1[:2]], "r1": [_pinned_copy(lib, a) for a in pr1[:2]],
+           "ed": [_pinned_copy(lib, a) for a in ped[:3]]}
+    pout = {c: _pinned_out(lib, pool_n * 64) for c in ("k1", "r1")}
+    pst = {c: _pinned_out(lib, pool_n) for c in ("k1", "r1")}
+    pval = _pinned_out(lib, pool_n)
+    sizes = [s for s in (64, 256, 1024, 4096, 16384, 65536, 262144, 1 << 20, 1 << 22, 1 << 24) if s <= args.sweep_max]
+    rows = []
+    for total in sizes:
+        m = total // 3
+        if m <= pool_n:
+            def calls():
+                t = []
+                t0 = time.perf_counter()
+                rc = lib.sigops_secp256k1_ecrecover(pin["k1"][0], pin["k1"][1], m, pout["k1"][0], pst["k1"][0])
+                t.append(time.perf_counter() - t0)
+                t0 = time.perf_counter()
+                rc |= lib.sigops_secp256r1_ecrecover(pin["r1"][0], pin["r1"][1], m, pout["r1"][0], pst["r1"][0])
+                t.append(time.perf_counter() - t0)
+                t0 = time.perf_counter()
+                rc |= lib.sigops_ed25519_ecverify(pin["ed"][0], pin["ed"][1], pin["ed"][2], m, pval[0])
+                t.append(time.perf_counter() - t0)
+                return rc, t
+
+            def check():
+                ok = (pout["k1"][1][: m * 64].reshape(m, 64) == pk1[2][:m]).all() and (pst["k1"][1][:m] == pk1[3][:m]).all()
+                ok = ok and (pout["r1"][1][: m * 64].reshape(m, 64) == pr1[2][:m]).all() and (pst["r1"][1][:m] == pr1[3][:m]).all()
+                return ok and (pval[1][:m] == ped[3][:m]).all()
+            bufs = "pinned"
+        else:
+            reps_t = (m + pool_n - 1) // pool_n
+
+            def tile(a):
+                return np.ascontiguousarray(np.tile(a, (reps_t,) + (1,) * (a.ndim - 1))[:m])
+            tk, tr, te = [tile(a) for a in pk1[:4]], [tile(a) for a in pr1[:4]], [tile(a) for a in ped[:4]]
+            ok1, os1 = np.empty((m, 64), np.uint8), np.empty(m, np.uint8)
+            or1, osr = np.empty((m, 64), np.uint8), np.empty(m, np.uint8)
+            ov = np.empty(m, np.uint8)
+
+            def calls():
+                t = []
+                t0 = time.perf_counter()
+                rc = lib.sigops_secp256k1_ecrecover(tk[0].ctypes.data, tk[1].ctypes.data, m, ok1.ctypes.data, os1.ctypes.data)
+                t.append(time.perf_counter() - t0)
+                t0 = time.perf_counter()
+                rc |= lib.sigops_secp256r1_ecrecover(tr[0].ctypes.data, tr[1].ctypes.data, m, or1.ctypes.data, osr.ctypes.data)
+                t.append(time.perf_counter() - t0)
+                t0 = time.perf_counter()
+                rc |= lib.sigops_ed25519_ecverify(te[0].ctypes.data, te[1].ctypes.data, te[2].ctypes.data, m, ov.ctypes.data)
+                t.append(time.perf_counter() - t0)
+                return rc, t
+
+            def check():
+                return ((ok1 == tk[2]).all() and (os1 == tk[3]).all() and (or1 == tr[2]).all() and (osr == tr[3]).all()
+                        and (ov == te[3]).all())
+            bufs = "pageable (numpy)"
+        nrep = 20 if total <= (1 << 20) else (6 if total <= (1 << 22) else 3)
+        for _ in range(2):
+            rc, _t = calls()
+            if rc != 0:
+                raise SystemExit("sweep: call failed: " + lib.sigops_last_error().decode())
+        per = {"k1": [], "r1": [], "ed": [], "all": []}
+        for _ in range(nrep):
+            rc, t = calls()
+            if rc != 0:
+                raise SystemExit("sweep: call failed: " + lib.sigops_last_error().decode())
+            per["k1"].append(t[0])
+            per["r1"].append(t[1])
+            per["ed"].append(t[2])
+            per["all"].append(sum(t))
+        if not check():
+            raise SystemExit(f"sweep n={total}: results differ from the expected values -- refusing to report")
+        rows.append({"n_total": total, "n_per_curve": m, "reps": nrep, "host_buffers": bufs,
+                     "latency_ms": {c: {"p50": _pct(per[c], 0.5) * 1e3, "p99": _pct(per[c], 0.99) * 1e3} for c in ("k1", "r1", "ed")},
+                     "sigs_per_s": 3 * m / _pct(per["all"], 0.5)})
+        log(f"[sweep] n={total}: k1 {rows[-1]['latency_ms']['k1']['p50']:.3f} r1 {rows[-1]['latency_ms']['r1']['p50']:.3f} "
+            f"ed {rows[-1]['latency_ms']['ed']['p50']:.3f} ms p50, {rows[-1]['sigs_per_s'] / 1e6:.2f} M sigs/s")
+    sweep = {"workload": "mixed k1 / r1 / ed25519 sweep, three back-to-back drop-in calls of n/3 signatures each (BASELINE config 5)",
+             "n_devices": G, "rows": rows,
+             "parity": "last repetition of every size: all rows bit-exact vs oracle-labelled batches (edge rows included)"}
+    for c in pin:
+        for ptr in pin[c]:
+            lib.sigops_host_free(ptr)
+    for d in (pout, pst):
+        for c in d:
+            lib.sigops_host_free(d[c][0])
+    lib.sigops_host_free(pval[0])
+    return strong, sweep, lib.sigops_kernel_launches() - l0
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
     """The reference's CPU path for this metric, timed on the host cores.  The Rust reference (fuel-crypto /
@@ -246,8 +444,10 @@ def run_sigops(args):
         raise SystemExit("bench.py: no CUDA device; the sigops path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")  # CPU-side rendezvous: waiting ranks must leave their GPUs idle
     lib = w.load()
     ids = (ctypes.c_int * 1)(local)
     rc = lib.sigops_init(ids, 1)
@@ -285,6 +485,7 @@ def run_sigops(args):
     sampler = None
     clocks = None
     launches_timed = 0
+    exec_macs, exec_note = executed_wide_macs()
     for curve in CURVES:
         if args.curves != "all" and curve not in args.curves.split(","):
             continue
@@ -377,6 +578,31 @@ def run_sigops(args):
         got = np.ctypeslib.as_array(ctypes.cast(p_out, ctypes.POINTER(ctypes.c_uint8)), shape=(out_bytes,))
         if not (got.reshape(exp.shape) == exp).all():
             raise SystemExit(f"{curve}: host-API result differs from the expected values -- refusing to report")
+        # ---- the same call with plain (pageable) numpy buffers: what `&Vec<...>` callers hand over ----
+        g_out = np.empty(out_bytes, dtype=np.uint8)
+        g_st = np.empty(n, dtype=np.uint8)
+
+        def pageable_call():
+            if is_ed:
+                rc = lib.sigops_ed25519_ecverify(sigs.ctypes.data, msgs.ctypes.data, pks.ctypes.data, n, g_out.ctypes.data)
+            elif curve == "secp256k1":
+                rc = lib.sigops_secp256k1_ecrecover(sigs.ctypes.data, msgs.ctypes.data, n, g_out.ctypes.data, g_st.ctypes.data)
+            else:
+                rc = lib.sigops_secp256r1_ecrecover(sigs.ctypes.data, msgs.ctypes.data, n, g_out.ctypes.data, g_st.ctypes.data)
+            if rc != 0:
+                raise SystemExit("host call (pageable) failed: " + lib.sigops_last_error().decode())
+
+        for _ in range(args.warmup):
+            pageable_call()
+        barrier()
+        l2 = lib.sigops_kernel_launches()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pageable_call()
+        pg_s = max_over_ranks(time.perf_counter() - t0)
+        n_l += lib.sigops_kernel_launches() - l2
+        if not (g_out.reshape(exp.shape) == exp).all():
+            raise SystemExit(f"{curve}: pageable host-API result differs from the expected values -- refusing to report")
         if curve == "secp256k1":
             clocks = sampler.stop(t_clock0, time.time())
         for ptr in (p_sigs, p_msgs, p_pks, p_out, p_st):
@@ -391,15 +617,21 @@ def run_sigops(args):
             "e2e": {"value": total / e2e_s, "unit": "sigs/s", "ms_per_step": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": n * (128 if is_ed else 96), "d2h_bytes_per_step": n if is_ed else n * 65,
                     "last_call_ms": {"h2d": h2d.value, "kernel": ker.value, "d2h": d2h.value}},
+            "e2e_pageable": {"value": total / pg_s, "unit": "sigs/s", "ms_per_step": pg_s / args.steps * 1e3,
+                             "vs_pinned": e2e_s / pg_s,
+                             "note": "same C-ABI call, plain numpy (malloc) buffers: the library stages them through its own "
+                                     "pinned ring with per-device copy threads"},
             "roofline": {"bound": "int32_imad", "achieved": achieved / 1e9, "peak": imad_peak / 1e9, "unit": "GIMAD/s",
                          "frac": achieved / imad_peak, "imad_eq_per_sig": IMAD_EQ[curve],
-                         "executed_imad_eq_per_sig": 2 * EXECUTED_WIDE_MACS[curve],
-                         "executed_frac": val / world * 2 * EXECUTED_WIDE_MACS[curve] / imad_peak,
+                         "executed_imad_eq_per_sig": 2 * exec_macs[curve] if exec_macs else None,
+                         "executed_frac": val / world * 2 * exec_macs[curve] / imad_peak if exec_macs else None,
+                         "executed_source": exec_note,
                          "hbm_frac": (val / world * HBM_BYTES[curve] / 1e9) / _hbm_peak()[0]},
             "parity": "bit-exact vs generator-expected outputs (all %d rows)" % n,
         }
         del d_sigs, d_msgs, d_pks, d_out, d_st
-        log(f"[rank {rank}] {curve}: {val / 1e6:.2f} M sigs/s kernel, {total / e2e_s / 1e6:.2f} M sigs/s e2e")
+        log(f"[rank {rank}] {curve}: {val / 1e6:.2f} M sigs/s kernel, {total / e2e_s / 1e6:.2f} M sigs/s e2e pinned, "
+            f"{total / pg_s / 1e6:.2f} M sigs/s e2e pageable")
 
     # ---- extension row: ed25519 `verify_strict` over the variable-length-message entry point,
     #      host C ABI, pinned buffers, same 1M batch (32-byte messages addressed through the offsets array) ----
@@ -522,6 +754,22 @@ def run_sigops(args):
         except Exception as e:  # the numbers are context only
             cpu["openssl_single_thread"] = {"unavailable": str(e)[:120]}
 
+    # ---- configs 4 and 5 as the drop-in call sees them: ONE process, ONE call, the library shards over all N devices.
+    #      Rank 0 re-initialises the pool with every device; the other ranks drop theirs and wait on the CPU (gloo). ----
+    strong = sweep = None
+    if not args.no_strong:
+        del flush
+        torch.cuda.synchronize()
+        lib.sigops_shutdown()
+        torch.cuda.empty_cache()
+        if world > 1:
+            dist.barrier(group=cpu_group)
+        if rank == 0:
+            strong, sweep, n_l = single_process_legs(lib, world, args, host_threads * world)
+            launches_timed += n_l
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
     if rank == 0:
         head = results.get("secp256k1") or next(iter(results.values()))
         hbm_peak, hbm_src = _hbm_peak()
@@ -546,6 +794,7 @@ def run_sigops(args):
                        "sharding": "contiguous shards, one process per GPU, no collective",
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)"},
             "e2e": {k: head["e2e"][k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+            "e2e_pageable": head["e2e_pageable"], "strong": strong, "sweep": sweep,
             "gpu_launches": int(launches_timed), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "curves": results, "extensions": ext,
         }
@@ -632,6 +881,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=131072)
     ap.add_argument("--ref-sample", type=int, default=65536)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the single-process strong-scaling and sweep legs")
+    ap.add_argument("--sweep-max", type=int, default=1 << 24, help="largest total batch of the config-5 sweep")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "sigops":
         log("note: --warmup < 3 breaks the timing rules; using 3")

@@ -250,7 +250,8 @@ enum {
      * are the INTERNAL, weakly reduced limbs (any value below 2^256), so that the once-in-2^31 fix-up paths can be hit */
     SIGOPS_UNIT_RAW_ADDSUB = 37,     /* in 17 (id, a, b)        out 16 : a+b, a-b as internal limbs     */
     SIGOPS_UNIT_RAW_REDUCE16 = 38,   /* in 17 (id, t[16])       out 8  : reduce16(t), ids 0 and 2 only  */
-    SIGOPS_UNIT_COUNT = 39
+    SIGOPS_UNIT_RAW_SHL = 39,        /* in 10 (id, K = 2|3, a)  out 8  : a * 2^K as internal limbs      */
+    SIGOPS_UNIT_COUNT = 40
 };
 
 #ifdef __cplusplus

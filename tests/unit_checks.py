@@ -94,6 +94,28 @@ def check_raw_fixups(U, nrand=400, seed=11):
     out = U.run_words("RAW_REDUCE16", np.array(rows, dtype=np.uint32))
     for (p, t), w in zip(meta, out):
         assert from_words(w) % p == t % p, hex(t)
+    # a * 2^K by one shift and one fold of the bits shifted out (the point doublings' 4x / 8x): crafted so that the fold's
+    # carry leaves the limbs the constant occupies and, above that, wraps past 2^256 once more
+    rows, meta = [], []
+    for fid, p, c, low_bits in fields:
+        for K in (2, 3):
+            for i in range(nrand):
+                ov = rng.randrange(1 << K) if i % 5 else (1 << K) - 1
+                kind = i % 4
+                if kind == 0:    # (a << K) mod 2^256 + o*c carries out of the constant's limbs
+                    low = (1 << low_bits) - 1 - rng.randrange(max(1, ov * c)) if low_bits < 256 else M - 1 - rng.randrange(ov * c + 1)
+                    body = (rng.getrandbits(256) >> low_bits << low_bits) | (low % (1 << min(low_bits, 256)))
+                elif kind == 1:  # ... and wraps past 2^256
+                    body = M - 1 - rng.randrange(max(1, ov * c))
+                else:
+                    body = rng.getrandbits(256)
+                body = body >> K << K  # the low K bits of a shifted value are zero
+                a = (ov << (256 - K)) | (body >> K)
+                rows.append([fid, K] + _w(a))
+                meta.append((p, K, a))
+    out = U.run_words("RAW_SHL", np.array(rows, dtype=np.uint32))
+    for (p, K, a), w in zip(meta, out):
+        assert from_words(w) % p == (a << K) % p, ("shl", K, hex(a))
 
 
 def _w(x, n=8):

@@ -134,9 +134,7 @@ SG_HD void jac_dbl(JacPoint& P) {
         F::sub(P.X, Fq, t);
         F::sub(t, D, P.X);
         F::mul(t, E, t);
-        F::dbl(Cc, Cc);
-        F::dbl(Cc, Cc);
-        F::dbl(Cc, Cc);
+        F::template shl<3>(Cc, Cc);  // 8C
         F::sub(P.Y, t, Cc);
     } else {
         Fe delta, gamma, beta, alpha, t, u;
@@ -153,16 +151,13 @@ SG_HD void jac_dbl(JacPoint& P) {
         F::sub(t, t, gamma);
         F::sub(P.Z, t, delta);
         F::sqr(t, alpha);
-        F::dbl(beta, beta);
-        F::dbl(beta, beta);  // 4*beta
-        F::dbl(u, beta);     // 8*beta
+        F::template shl<2>(beta, beta);  // 4*beta
+        F::dbl(u, beta);                 // 8*beta
         F::sub(P.X, t, u);
         F::sub(t, beta, P.X);
         F::mul(t, alpha, t);
         F::sqr(gamma, gamma);
-        F::dbl(gamma, gamma);
-        F::dbl(gamma, gamma);
-        F::dbl(gamma, gamma);
+        F::template shl<3>(gamma, gamma);  // 8*gamma^2
         F::sub(P.Y, t, gamma);
     }
 }

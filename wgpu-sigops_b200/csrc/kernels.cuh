@@ -187,6 +187,10 @@ SG_HD void unit_shape(int op, int& in_w, int& out_w) {
             in_w = 17;
             out_w = 8;
             break;
+        case SIGOPS_UNIT_RAW_SHL:
+            in_w = 10;
+            out_w = 8;
+            break;
         default:
             break;
     }
@@ -201,6 +205,17 @@ SG_HD void unit_raw_addsub(u32* out, const u32* in) {
     F::sub(d, a, b);
     copy8(out, s.v);
     copy8(out + 8, d.v);
+}
+
+template <class F>
+SG_HD void unit_raw_shl(u32* out, const u32* in) {
+    Fe a, r;
+    copy8(a.v, in + 1);
+    if (in[0] == 2)
+        F::template shl<2>(r, a);
+    else
+        F::template shl<3>(r, a);
+    copy8(out, r.v);
 }
 
 template <class F>
@@ -351,6 +366,11 @@ SG_HD void unit_dispatch(int op, u32* out, const u32* in, const TabRef& tab, con
         case SIGOPS_UNIT_RAW_REDUCE16:
             if (in[0] == 0) FpK1::reduce16(out, in + 1);
             else Fp25519::reduce16(out, in + 1);
+            break;
+        case SIGOPS_UNIT_RAW_SHL:
+            if (in[0] == 0) unit_raw_shl<FpK1>(out, in + 1);
+            else if (in[0] == 1) unit_raw_shl<FpR1>(out, in + 1);
+            else unit_raw_shl<Fp25519>(out, in + 1);
             break;
         case SIGOPS_UNIT_MUL8X8:
             mul8x8(out, in, in + 8);

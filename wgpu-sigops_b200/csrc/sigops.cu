@@ -401,12 +401,14 @@ int env_int(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-// Launch geometry.  One signature per thread per pass; a launch of n signatures runs P = ceil(n / (SMs x 512)) passes, and
-// the block size is BALANCED over them: tpb = ceil(n / (SMs x P)) rounded up to a warp, one block per SM.  A pass costs
-// about the same whether 12 or 16 warps per SM run it, so 1.73 waves run as two passes of 14 warps (and share their
-// inversions, curve_sw.cuh) instead of one full pass plus a 73%-empty one.  Small batches (P = 1) are spread over all SMs
-// with proportionally smaller blocks instead of filling a few SMs to the brim (latency of the 64 ... 64k end of the sweep).
-// SIGOPS_BALANCED=0 restores round 1's geometry (full 512-thread blocks once the batch covers the device).
+// Launch geometry: full 512-thread blocks (one per SM, all 16 warps phase-locked by the kernels' barriers) once the batch
+// covers the device; smaller batches are spread over all SMs with proportionally smaller blocks instead of filling a few
+// SMs to the brim (latency of the 64 ... 64k end of the batch-size sweep).
+// A pass costs about 0.31 + 0.38 k ms (secp256k1) with k = warps per scheduler = ceil(warps per SM / 4): the block's
+// barriers make the most loaded scheduler set the pace, so 13 and 16 warps per SM take the same time.  That is why
+// balancing a shard of w.f waves over ceil(w.f) equal passes (SIGOPS_BALANCED=1: tpb = ceil(n / (SMs x P)) rounded to a
+// warp) measured SLOWER than full passes plus a separate, smaller tail launch (profiles/r02_geometry.txt: 131,072
+// signatures 3.41 vs 3.28 ms, 262,144 6.60 vs 6.11 ms); it stays selectable for the record, off by default.
 void launch_geometry(const Device& d, Op op, size_t n, int* grid, int* tpb_out) {
     const int max_g = op == OP_K1 ? d.grid_k1 : op == OP_R1 ? d.grid_r1 : d.grid_ed;
     const size_t wave = (size_t)d.sms * kBlock;
@@ -415,7 +417,7 @@ void launch_geometry(const Device& d, Op op, size_t n, int* grid, int* tpb_out) 
     if (n < wave) {
         size_t per_sm = (n + d.sms - 1) / d.sms;
         tpb = (int)std::min<size_t>(kBlock, std::max<size_t>(32, (per_sm + 31) / 32 * 32));
-    } else if (env_int("SIGOPS_BALANCED", 1) != 0) {
+    } else if (env_int("SIGOPS_BALANCED", 0) != 0) {
         passes = (n + wave - 1) / wave;
         size_t per_sm = (n + (size_t)d.sms * passes - 1) / ((size_t)d.sms * passes);
         tpb = (int)std::min<size_t>(kBlock, std::max<size_t>(32, (per_sm + 31) / 32 * 32));
@@ -426,13 +428,16 @@ void launch_geometry(const Device& d, Op op, size_t n, int* grid, int* tpb_out) 
     *tpb_out = tpb;
 }
 
-// Round 1's alternative for shards of w.f waves: launch the partial wave on its own behind the whole ones
-// (SIGOPS_TAIL_SPLIT=1; off by default since the balanced geometry above covers the case in one launch).
+// A launch of w.f waves (one wave = SMs x 512 signatures, one per thread) costs ceil(w.f) full passes: the last, partial
+// pass runs every thread (rows past the end are clamped) at 16 warps per SM.  When the tail is at most
+// kTailSplitNum/kTailSplitDen of a wave it is launched on its own right behind the main part, with the small-batch
+// geometry: fewer warps per scheduler finish a pass sooner.  Matters for shards of one to a few waves -- the 1M block
+// cut over 4 or 8 GPUs, the middle of the batch-size sweep.  SIGOPS_TAIL_SPLIT=0 disables it.
 constexpr size_t kTailSplitNum = 3, kTailSplitDen = 4;
 size_t tail_split(const Device& d, size_t n) {  // signatures in the main launch (n if no split)
     const size_t wave = (size_t)d.sms * kBlock;
     if (n < wave) return n;
-    if (env_int("SIGOPS_TAIL_SPLIT", 0) == 0) return n;
+    if (env_int("SIGOPS_TAIL_SPLIT", 1) == 0 || env_int("SIGOPS_BALANCED", 0) != 0) return n;
     const size_t tail = n % wave;
     if (tail == 0 || tail * kTailSplitDen > wave * kTailSplitNum) return n;
     return n - tail;
