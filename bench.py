@@ -393,13 +393,17 @@ def run_reference(args):
     sample = args.ref_sample
     sigs, msgs, _, exp = make_batch("secp256k1", sample, sample, 0x51600002, threads)
     for _ in range(max(args.warmup, 1)):
-        coracle.ecrecover(0, sigs[:4096], msgs[:4096], threads=threads)
+        coracle.k1_ecrecover_fast(sigs[:4096], msgs[:4096], threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out, st = coracle.ecrecover(0, sigs, msgs, threads=threads)
+        out, st = coracle.k1_ecrecover_fast(sigs, msgs, threads=threads)
     dt = time.perf_counter() - t0
     assert (out == exp).all() and not st.any()
     val = sample * args.steps / dt
+    t0 = time.perf_counter()
+    o_chk, st_chk = coracle.ecrecover(0, sigs, msgs, threads=threads)  # the checker (generic Montgomery, no endomorphism)
+    checker_val = sample / (time.perf_counter() - t0)
+    assert (o_chk == out).all()
     extra = {}
     for curve in ("secp256r1", "ed25519"):
         s2, m2, p2, e2 = make_batch(curve, sample // 2, sample // 2, 0x51600002, threads)
@@ -418,9 +422,12 @@ def run_reference(args):
         "config": {"workload": "secp256k1 ecrecover, 1M-signature block per GPU (BASELINE config 4)",
                    "sample_per_step": sample, "note": "CPU arm: each step is a bounded sample of the workload"},
         "cpu_baseline": {"value": val, "unit": "sigs/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} random valid secp256k1 signatures per step, oracle/sigops_oracle.c, "
-                                   f"{threads} pthreads; the Rust reference (fuel-crypto -> libsecp256k1) is not "
-                                   "buildable here (no rustc)"},
+                         "per_thread": val / threads, "checker_value": checker_val,
+                         "openssl": _openssl_native(coracle, threads, sigs, msgs, exp),
+                         "sample": f"{sample} random valid secp256k1 signatures per step, oracle/k1_fast.c (2^256-2^32-977 "
+                                   f"fold field, GLV, wNAF Strauss: the algorithm class of libsecp256k1), {threads} pthreads; "
+                                   "checker_value = oracle/sigops_oracle.c (generic Montgomery, no endomorphism) on the same "
+                                   "sample; the Rust reference (fuel-crypto -> libsecp256k1) is not buildable here (no rustc)"},
         "e2e": {"value": val, "unit": "sigs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "curves": extra, "gpu_launches": 0,
     }
@@ -732,19 +739,26 @@ def run_sigops(args):
         threads = coracle.host_threads()
         sample = args.cpu_sample
         s, m, _, e = make_batch("secp256k1", sample, sample, 0x51600002, threads)
-        coracle.ecrecover(0, s[:2048], m[:2048], threads=threads)
+        coracle.k1_ecrecover_fast(s[:2048], m[:2048], threads=threads)
         t0 = time.perf_counter()
-        o, st = coracle.ecrecover(0, s, m, threads=threads)
+        o, st = coracle.k1_ecrecover_fast(s, m, threads=threads)
         dt = time.perf_counter() - t0
         assert (o == e).all()
         t0 = time.perf_counter()
-        coracle.ecrecover(0, s[:4096], m[:4096], threads=1)
+        coracle.k1_ecrecover_fast(s[:8192], m[:8192], threads=1)
         dt1 = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        o2, _ = coracle.ecrecover(0, s[:32768], m[:32768], threads=threads)
+        dtc = time.perf_counter() - t0
+        assert (o2 == e[:32768]).all()
         cpu = {"value": sample / dt, "unit": "sigs/s", "cores": threads, "kind": "port",
-               "single_thread_value": 4096 / dt1,
-               "sample": f"{sample} of the same random valid secp256k1 signatures, oracle/sigops_oracle.c (generic "
-                         f"4x64 Montgomery, wNAF Strauss-Shamir), {threads} pthreads; the Rust reference CPU path "
-                         "(fuel-crypto -> libsecp256k1) cannot be built here (no rustc)"}
+               "single_thread_value": 8192 / dt1, "checker_value": 32768 / dtc,
+               "openssl": _openssl_native(coracle, threads, s, m, e),
+               "sample": f"{sample} of the same random valid secp256k1 signatures, oracle/k1_fast.c (2^256-2^32-977 fold "
+                         f"field, GLV, wNAF Strauss: the algorithm class of libsecp256k1), {threads} pthreads; "
+                         "checker_value = oracle/sigops_oracle.c (generic 4x64 Montgomery, no endomorphism: what labels the "
+                         "test batches); the Rust reference CPU path (fuel-crypto -> libsecp256k1) cannot be built here "
+                         "(no rustc)"}
 
     # Independent production-grade reference points on the same host cores: OpenSSL 3 (via `cryptography`) single-thread
     # ECDSA *verify* on P-256 / secp256k1 and Ed25519 verify -- "verify, not recover; OpenSSL, not fuel-crypto" (BASELINE.md 3).
@@ -803,6 +817,31 @@ def run_sigops(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def _openssl_native(coracle, threads: int, k1_sigs, k1_msgs, k1_pks, n: int = 32768):
+    """OpenSSL 3 libcrypto called natively (oracle/openssl_ref.c) on `threads` pthreads -- the same core count as the port:
+    ECDSA verify on secp256k1 (the same signatures, the signers' keys) and P-256, Ed25519 verify.  Context, not a target:
+    "verify, not recover; OpenSSL, not fuel-crypto" (BASELINE.md section 3 item 2)."""
+    if coracle.openssl_ref() is None:
+        return {"unavailable": "libcrypto could not be linked (oracle/_build/ossl.log)"}
+    out = {"cores": threads, "unit": "verifies/s", "note": "native libcrypto, verify (not recover), same host threads as the port"}
+    n = min(n, len(k1_sigs))
+    t0 = time.perf_counter()
+    ok = coracle.openssl_ecdsa_verify(0, k1_sigs[:n], k1_msgs[:n], k1_pks[:n], threads=threads)
+    out["secp256k1_ecdsa_verify"] = n / (time.perf_counter() - t0)
+    assert ok.all()
+    s, m, pk = coracle.gen_ecdsa(1, n, seed=0x51600009, low_s=True, threads=threads)
+    t0 = time.perf_counter()
+    ok = coracle.openssl_ecdsa_verify(1, s, m, pk, threads=threads)
+    out["p256_ecdsa_verify"] = n / (time.perf_counter() - t0)
+    assert ok.all()
+    s, m, pk = coracle.gen_ed25519(n, seed=0x5160000A, threads=threads)
+    t0 = time.perf_counter()
+    ok = coracle.openssl_ed25519_verify(s, m, pk, threads=threads)
+    out["ed25519_verify"] = n / (time.perf_counter() - t0)
+    assert ok.all()
+    return out
 
 
 def _openssl_points(reps: int = 1500):

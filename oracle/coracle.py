@@ -27,13 +27,13 @@ def _cpu_model() -> str:
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(HERE, "sigops_oracle.c")
+    srcs = [os.path.join(HERE, f) for f in ("sigops_oracle.c", "k1_fast.c", "openssl_ref.c", "Makefile")]
     cpu = _cpu_model()
     fresh = (
         os.path.exists(SO)
         and os.path.exists(STAMP)
         and open(STAMP).read() == cpu
-        and os.path.getmtime(SO) >= os.path.getmtime(src)
+        and all(os.path.getmtime(SO) >= os.path.getmtime(f) for f in srcs)
     )
     if force or not fresh:
         subprocess.check_call(["make", "-s", "-B", "-C", HERE])
@@ -54,6 +54,7 @@ def load() -> ctypes.CDLL:
         lib.oracle_sha512.argtypes = [vp, sz, vp]
         lib.oracle_ed25519_verify_msgs.argtypes = [vp, vp, vp, vp, sz, i32, vp]
         lib.oracle_ed25519_sign.argtypes = [vp, vp, sz, vp, vp]
+        lib.oracle_k1_ecrecover_fast.argtypes = [vp, vp, sz, vp, vp, i32]
         _lib = lib
     return _lib
 
@@ -85,6 +86,65 @@ def ecrecover(curve: int, sigs, msgs, threads: int = 0):
                                      threads or host_threads())
         assert rc == 0
     return out, st
+
+
+def k1_ecrecover_fast(sigs, msgs, threads: int = 0):
+    """secp256k1 recovery by oracle/k1_fast.c (special-prime field, GLV, wNAF: the algorithm class of libsecp256k1) -- the
+    timed CPU baseline of bench.py; pinned to `ecrecover(0, ...)` by tests/test_oracle.py."""
+    sigs, msgs = _u8(sigs, 64), _u8(msgs, 32)
+    n = sigs.shape[0]
+    assert msgs.shape[0] == n
+    out = np.zeros((n, 64), dtype=np.uint8)
+    st = np.zeros(n, dtype=np.uint8)
+    if n:
+        rc = load().oracle_k1_ecrecover_fast(sigs.ctypes.data, msgs.ctypes.data, n, out.ctypes.data, st.ctypes.data,
+                                             threads or host_threads())
+        assert rc == 0
+    return out, st
+
+
+_ossl = None
+
+
+def openssl_ref():
+    """libosslref.so (oracle/openssl_ref.c: OpenSSL 3 verify legs) or None when libcrypto could not be linked."""
+    global _ossl
+    if _ossl is None:
+        build()
+        path = os.path.join(HERE, "_build", "libosslref.so")
+        if not os.path.exists(path):
+            _ossl = False
+        else:
+            try:
+                lib = ctypes.CDLL(path)
+                vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+                lib.openssl_ecdsa_verify.argtypes = [i32, vp, vp, vp, sz, vp, i32]
+                lib.openssl_ed25519_verify.argtypes = [vp, vp, vp, sz, vp, i32]
+                _ossl = lib
+            except OSError:
+                _ossl = False
+    return _ossl or None
+
+
+def openssl_ecdsa_verify(curve: int, sigs, msgs, pubkeys, threads: int = 0):
+    """OpenSSL ECDSA verify of Fuel-encoded signatures against the given 64-byte keys; returns uint8 verdicts."""
+    lib = openssl_ref()
+    sigs, msgs, pks = _u8(sigs, 64), _u8(msgs, 32), _u8(pubkeys, 64)
+    ok = np.zeros(sigs.shape[0], dtype=np.uint8)
+    if sigs.shape[0]:
+        lib.openssl_ecdsa_verify(curve, sigs.ctypes.data, msgs.ctypes.data, pks.ctypes.data, sigs.shape[0], ok.ctypes.data,
+                                 threads or host_threads())
+    return ok
+
+
+def openssl_ed25519_verify(sigs, msgs, pks, threads: int = 0):
+    lib = openssl_ref()
+    sigs, msgs, pks = _u8(sigs, 64), _u8(msgs, 32), _u8(pks, 32)
+    ok = np.zeros(sigs.shape[0], dtype=np.uint8)
+    if sigs.shape[0]:
+        lib.openssl_ed25519_verify(sigs.ctypes.data, msgs.ctypes.data, pks.ctypes.data, sigs.shape[0], ok.ctypes.data,
+                                   threads or host_threads())
+    return ok
 
 
 def ecverify_ed25519(sigs, msgs, pks, threads: int = 0):

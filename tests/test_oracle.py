@@ -330,3 +330,43 @@ def test_precompute_bases_golden():
     limbs = o.precompute_bases("secp256k1", 13)
     x = sum(v << (13 * i) for i, v in enumerate(limbs[:20]))
     assert x == o.K1.gx * (1 << 260) % o.K1.p
+
+
+def test_fast_k1_port_is_pinned_to_the_checker():
+    """oracle/k1_fast.c (the timed CPU baseline: fold field, GLV, wNAF) against the checker oracle_ecrecover on random valid
+    signatures (low-s and high-s), the whole secp256k1 edge corpus, single-bit corruptions and mostly-invalid fuzz rows."""
+    import batches
+    import fuzz_cases
+
+    s, m, pk, st, n_edge = batches.ecdsa_batch(0, 6000, edge_every=3, seed=77, mix_high_s=True)
+    o1, s1 = coracle.k1_ecrecover_fast(s, m, threads=2)
+    assert n_edge > 1900 and st.sum() > 300
+    assert (o1 == pk).all() and (s1 == st).all()
+    rows = [(x[1], x[2]) for x in uc.ecdsa_cases(o.K1, nvalid=50)]
+    sig = np.array([np.frombuffer(a, dtype=np.uint8) for a, _ in rows])
+    msg = np.array([np.frombuffer(b, dtype=np.uint8) for _, b in rows])
+    e_out, e_st = coracle.ecrecover(0, sig, msg)
+    f_out, f_st = coracle.k1_ecrecover_fast(sig, msg, threads=1)
+    assert (e_out == f_out).all() and (e_st == f_st).all()
+    fs, fm = fuzz_cases.ecdsa_batch(0, 8000, seed=5)
+    e_out, e_st = coracle.ecrecover(0, fs, fm)
+    f_out, f_st = coracle.k1_ecrecover_fast(fs, fm, threads=2)
+    assert 1000 < e_st.sum() < 7000
+    assert (e_out == f_out).all() and (e_st == f_st).all()
+
+
+def test_openssl_native_legs_agree_with_the_oracle():
+    """oracle/openssl_ref.c (bench.py's OpenSSL baseline legs): every key the oracle recovers verifies, a corrupted message
+    does not; Ed25519 verdicts equal the oracle's on the edge corpus (OpenSSL is cofactorless with the same s < L rule)."""
+    import batches
+
+    if coracle.openssl_ref() is None:
+        pytest.skip("libcrypto not linkable")
+    for cid in (0, 1):
+        s, m, pk, st, _ = batches.ecdsa_batch(cid, 600, edge_every=0, seed=91 + cid, mix_high_s=(cid == 1))
+        assert coracle.openssl_ecdsa_verify(cid, s, m, pk, threads=2).all()
+        m2 = m.copy()
+        m2[:, 5] ^= 1
+        assert not coracle.openssl_ecdsa_verify(cid, s, m2, pk, threads=2).any()
+    s, m, pk, v, _ = batches.ed25519_batch(900, edge_every=2, seed=93)
+    assert (coracle.openssl_ed25519_verify(s, m, pk, threads=2) == v).all()
