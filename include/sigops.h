@@ -251,7 +251,11 @@ enum {
     SIGOPS_UNIT_RAW_ADDSUB = 37,     /* in 17 (id, a, b)        out 16 : a+b, a-b as internal limbs     */
     SIGOPS_UNIT_RAW_REDUCE16 = 38,   /* in 17 (id, t[16])       out 8  : reduce16(t), ids 0 and 2 only  */
     SIGOPS_UNIT_RAW_SHL = 39,        /* in 10 (id, K = 2|3, a)  out 8  : a * 2^K as internal limbs      */
-    SIGOPS_UNIT_COUNT = 40
+    /* the lane-group kernels' twins (several cooperating threads per item, complete projective / four-way Edwards formulas) */
+    SIGOPS_UNIT_K1_GROUP_DOUBLE_MUL = 40, /* in 32 (u1,u2,x,y)  out 17 : u1*G + u2*(x,y)                */
+    SIGOPS_UNIT_R1_GROUP_DOUBLE_MUL = 41,
+    SIGOPS_UNIT_ED_GROUP_MULPT = 42,      /* in 24 (k, x, y)    out 16 : k*(x,y) affine x,y             */
+    SIGOPS_UNIT_COUNT = 43
 };
 
 #ifdef __cplusplus

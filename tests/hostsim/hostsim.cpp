@@ -7,7 +7,12 @@
 #include <algorithm>
 #include <cstring>
 #include <vector>
+#include <pthread.h>
+
+#include <thread>
+
 #include "../../wgpu-sigops_b200/csrc/kernels.cuh"
+#include "../../wgpu-sigops_b200/csrc/group.cuh"
 
 using namespace sigops;
 
@@ -26,9 +31,108 @@ static void ensure_tables() {
     }
 }
 
+// ---- lane-group emulation: the roles of a signature are OS threads meeting at a pthread barrier (GroupCtx::sync) and
+//      sharing the mailbox / table arrays exactly as the warps of a block share them in shared memory ----
+struct GroupShared {
+    std::vector<Q4> mb;
+    std::vector<u32> sc;
+    std::vector<Q4> tab;
+    pthread_barrier_t bar;
+    int roles;
+    explicit GroupShared(int roles_, int tab_chunks)
+        : mb((size_t)kMbSlots * 2 * kGroupSigs), sc((size_t)kScWords * kGroupSigs), tab((size_t)tab_chunks * kGroupSigs), roles(roles_) {
+        pthread_barrier_init(&bar, nullptr, (unsigned)roles);
+    }
+    ~GroupShared() { pthread_barrier_destroy(&bar); }
+    GroupCtx ctx(int role) {
+        GroupCtx g;
+        g.role = role;
+        g.mb = mb.data();
+        g.sc = sc.data();
+        g.host_sync = [](void* b) { pthread_barrier_wait((pthread_barrier_t*)b); };
+        g.host_arg = &bar;
+        return g;
+    }
+    TabRef tabref() { return TabRef{tab.data(), (u32)kGroupSigs}; }
+    template <class Fn>
+    void run(Fn fn) {  // fn(role, ctx) on `roles` threads
+        std::vector<std::thread> th;
+        for (int r = 1; r < roles; r++) th.emplace_back([&, r] { fn(r, ctx(r)); });
+        fn(0, ctx(0));
+        for (auto& t : th) t.join();
+    }
+};
+
 extern "C" {
 
+int hostsim_group_unit(int op, const uint32_t* in, size_t n, uint32_t* out) {
+    ensure_tables();
+    int in_w, out_w;
+    unit_shape(op, in_w, out_w);
+    const bool ed = op == SIGOPS_UNIT_ED_GROUP_MULPT;
+    GroupShared sh(ed ? kGroupRolesEd : kGroupRolesSw, kGroupSwTabChunks);
+    sh.run([&](int, GroupCtx g) {
+        TabRef tab = sh.tabref();
+        for (size_t i = 0; i < n; i++) {
+            u32 a[32], r[17];
+            for (int j = 0; j < 32; j++) a[j] = j < in_w ? in[i * in_w + j] : 0u;
+            for (int j = 0; j < 17; j++) r[j] = 0;
+            bool writer;
+            if (op == SIGOPS_UNIT_K1_GROUP_DOUBLE_MUL)
+                writer = unit_double_mul_g<CurveK1>(r, a, a + 8, a + 16, tab, k1_gtab.data(), g);
+            else if (op == SIGOPS_UNIT_R1_GROUP_DOUBLE_MUL)
+                writer = unit_double_mul_g<CurveR1>(r, a, a + 8, a + 16, tab, r1_gtab.data(), g);
+            else
+                writer = unit_ed_mulpt_g(r, a, tab, g);
+            if (writer)
+                for (int j = 0; j < out_w; j++) out[i * out_w + j] = r[j];
+            g.sync();
+        }
+    });
+    return 0;
+}
+
+int hostsim_group_ecrecover(int curve, const uint8_t* sigs, const uint8_t* msgs, size_t n, uint8_t* out, uint8_t* status) {
+    ensure_tables();
+    GroupShared sh(kGroupRolesSw, kGroupSwTabChunks);
+    sh.run([&](int, GroupCtx g) {
+        TabRef tab = sh.tabref();
+        for (size_t i = 0; i < n; i++) {
+            u32 sig_w[16], msg_w[8], out_w[16], st = 0;
+            memcpy(sig_w, sigs + 64 * i, 64);
+            memcpy(msg_w, msgs + 32 * i, 32);
+            const bool writer = curve == 0 ? sw_ecrecover_group<CurveK1>(sig_w, msg_w, out_w, &st, tab, k1_gtab.data(), g)
+                                           : sw_ecrecover_group<CurveR1>(sig_w, msg_w, out_w, &st, tab, r1_gtab.data(), g);
+            if (writer) {
+                memcpy(out + 64 * i, out_w, 64);
+                if (status) status[i] = (uint8_t)st;
+            }
+            g.sync();
+        }
+    });
+    return 0;
+}
+
+int hostsim_group_ed25519_verify(const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n, uint8_t* valid) {
+    ensure_tables();
+    GroupShared sh(kGroupRolesEd, kGroupEdTabChunks);
+    sh.run([&](int role, GroupCtx g) {
+        TabRef tab = sh.tabref();
+        for (size_t i = 0; i < n; i++) {
+            u32 sig_w[16], msg_w[8], pk_w[8];
+            memcpy(sig_w, sigs + 64 * i, 64);
+            memcpy(msg_w, msgs + 32 * i, 32);
+            memcpy(pk_w, pks + 32 * i, 32);
+            const u32 v = ed_verify_group(sig_w, msg_w, pk_w, tab, ed_btab.data(), g);
+            if (role == 0) valid[i] = (uint8_t)v;
+            g.sync();
+        }
+    });
+    return 0;
+}
+
 int hostsim_unit(int op, const uint32_t* in, size_t n, uint32_t* out) {
+    if (op >= SIGOPS_UNIT_K1_GROUP_DOUBLE_MUL) return hostsim_group_unit(op, in, n, out);
     ensure_tables();
     int in_w, out_w;
     unit_shape(op, in_w, out_w);

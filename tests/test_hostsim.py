@@ -89,3 +89,39 @@ def test_fuzz_builders_through_host_simulation():
     lib.hostsim_ed25519_verify(sigs.tobytes(), msgs.tobytes(), pks.tobytes(), n, got.ctypes.data)
     assert not (got != exp).any()
     assert 0.05 < exp.mean() < 0.4
+
+
+def test_lanegroup_units(sim_units):
+    """group.cuh through a thread-per-role emulation (pthread barrier = the block barrier, shared arrays = shared memory)."""
+    uc.check_group_curves(sim_units, n=10)
+
+
+def test_lanegroup_ecrecover_and_verify_logic():
+    """The lane-group programs end to end on the whole edge corpus and on fuzz rows, against the oracle."""
+    import coracle
+    import fuzz_cases
+
+    lib = load_hostsim()
+    for cid, c in ((0, o.K1), (1, o.R1)):
+        cases = uc.ecdsa_cases(c, nvalid=12)
+        n = len(cases)
+        out = np.zeros((n, 64), dtype=np.uint8)
+        st = np.zeros(n, dtype=np.uint8)
+        lib.hostsim_group_ecrecover(cid, b"".join(x[1] for x in cases), b"".join(x[2] for x in cases), n, out.ctypes.data, st.ctypes.data)
+        uc.check_ecrecover_against_oracle(c, cases, out, st)
+        sigs, msgs = fuzz_cases.ecdsa_batch(cid, 600, seed=9)
+        exp_out, exp_st = coracle.ecrecover(cid, sigs, msgs)
+        out = np.zeros((600, 64), dtype=np.uint8)
+        st = np.zeros(600, dtype=np.uint8)
+        lib.hostsim_group_ecrecover(cid, sigs.tobytes(), msgs.tobytes(), 600, out.ctypes.data, st.ctypes.data)
+        assert not (st != exp_st).any() and not (out != exp_out).any()
+    cases = uc.ed_cases(nvalid=12)
+    n = len(cases)
+    got = np.zeros(n, dtype=np.uint8)
+    lib.hostsim_group_ed25519_verify(b"".join(x[1] for x in cases), b"".join(x[2] for x in cases), b"".join(x[3] for x in cases), n, got.ctypes.data)
+    uc.check_ed_against_oracle(cases, got)
+    sigs, msgs, pks = fuzz_cases.ed25519_batch(600, seed=9)
+    exp = coracle.ecverify_ed25519(sigs, msgs, pks)
+    got = np.zeros(600, dtype=np.uint8)
+    lib.hostsim_group_ed25519_verify(sigs.tobytes(), msgs.tobytes(), pks.tobytes(), 600, got.ctypes.data)
+    assert not (got != exp).any()

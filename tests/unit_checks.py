@@ -264,6 +264,60 @@ def check_curves(U, n=12, seed=7):
         assert (from_words(w[:8]), from_words(w[8:16])) == e
 
 
+def check_group_curves(U, n=12, seed=17):
+    """The lane-group kernels' double-scalar multiplication (complete projective formulas, cooperating roles) and the
+    four-role Edwards ladder through their unit shims: the reference's Strauss-Shamir corner case, R = +-G, a sum that is the
+    point at infinity, zero scalars, random inputs."""
+    rng = random.Random(seed)
+    x = 0x8CE48A1B5F7942ED63C3F5380D98BD57F702AA6DED0E8022B4890762ACA5FA5D
+    y = 0x84023F2E9587339FE4076DE927D8F1CBFF4279A6982E1B0599221E20153F147A
+    bx = 57955212013049338432744149260690748736552621582696778344469660993364486735760
+    by = 18014696949887157897072847726343716132385694929890630512424732633979399864330
+    w = U.run("K1_GROUP_DOUBLE_MUL", [(x, y, bx, by)])[0]
+    G = (o.K1.gx, o.K1.gy)
+    exp = o.sw_add(o.K1, o.sw_mul(o.K1, x, G), o.sw_mul(o.K1, y, (bx, by)))
+    assert w[16] == 0 and (from_words(w[:8]), from_words(w[8:16])) == exp
+    for name, c in (("K1", o.K1), ("R1", o.R1)):
+        G = (c.gx, c.gy)
+        items, exps = [], []
+        for i in range(n):
+            u1, u2 = rng.getrandbits(256) % c.n, rng.getrandbits(256) % c.n
+            kk = rng.getrandbits(256) % (c.n - 1) + 1
+            if i == 0:
+                kk = 1  # R = G
+            if i == 1:
+                kk = c.n - 1  # R = -G
+            if i == 2:
+                u1, u2, kk = 5, 5, c.n - 1  # u1*G + u2*(-G) = infinity
+            if i == 3:
+                u2 = 0
+            if i == 4:
+                u1 = 0
+            if i == 5:
+                u1, u2 = 0, 0
+            if i == 6:
+                u1, u2, kk = c.n - 1, 1, 1  # -G + G
+            if i == 7:
+                u1, u2, kk = 1, 1, 1  # G + G: the addition degenerates into a doubling
+            P = o.sw_mul(c, kk, G)
+            items.append((u1, u2, P[0], P[1]))
+            exps.append(o.sw_add(c, o.sw_mul(c, u1, G), o.sw_mul(c, u2, P)))
+        for e, w in zip(exps, U.run(name + "_GROUP_DOUBLE_MUL", items)):
+            if e is None:
+                assert w[16] == 1
+            else:
+                assert w[16] == 0 and (from_words(w[:8]), from_words(w[8:16])) == e
+    items, exps = [], []
+    for i in range(n):
+        k = rng.getrandbits(256) % o.ED_L
+        px, py = _affine_ed(o.ed_mul(rng.getrandbits(256) % o.ED_L, o.ED_B))
+        k = [0, 1, 2**256 - 1, 8][i] if i < 4 else k
+        items.append((k, px, py))
+        exps.append(_affine_ed(o.ed_mul(k, (px, py, 1, px * py % o.ED_P))))
+    for e, w in zip(exps, U.run("ED_GROUP_MULPT", items)):
+        assert (from_words(w[:8]), from_words(w[8:16])) == e
+
+
 def ecdsa_cases(c, nvalid=40):
     cases = o.ecdsa_edge_cases(c)
     for i in range(nvalid):

@@ -6,6 +6,13 @@
 // (`add.cc/addc.cc`, `mad.lo.cc/madc.hi.cc`).  ptxas fuses each lo/hi pair into one
 // IMAD.WIDE.U32(.X) with the carry in a predicate register (see profiles/sass_*.txt).
 //
+// Every output operand of a multi-instruction asm block is EARLY-CLOBBER ("=&r" / "+&r").  Without it the compiler may let
+// an output (in particular the tied input of a read-write accumulator) share a virtual register with another input that
+// holds the same value -- e.g. a zero-initialised accumulator limb and a compile-time-zero limb of an operand -- and the
+// block then overwrites that input before a later instruction of the same block reads it.  Seen with a squaring of the
+// constant 1 (Z of an affine point) inlined into the lane-group kernels: all eight diagonal products read limb 0
+// (tools/proto/sqr_one.cu, profiles/r02_variants.md).
+//
 // Every primitive has two bodies: inline PTX under __CUDA_ARCH__ (the product) and a
 // portable uint64_t body used only when the same headers are compiled for the host by
 // tests/hostsim (logic tests without a GPU) and by the CPU-only precompute_bases table
@@ -54,7 +61,7 @@ SG_HD u32 add8(u32* r, const u32* a, const u32* b) {
         "addc.cc.u32 %6, %15, %23;\n\t"
         "addc.cc.u32 %7, %16, %24;\n\t"
         "addc.u32 %8, 0, 0;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(c)
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
           "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
 #else
@@ -82,7 +89,7 @@ SG_HD u32 sub8(u32* r, const u32* a, const u32* b) {
         "subc.cc.u32 %6, %15, %23;\n\t"
         "subc.cc.u32 %7, %16, %24;\n\t"
         "subc.u32 %8, 0, 0;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "=&r"(r[0]), "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(c)
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
           "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
     c &= 1u;  // subc.u32 x,0,0 yields 0 or 0xffffffff
@@ -111,7 +118,7 @@ SG_HD u32 add8_small(u32* r, u32 lo, u32 hi) {
         "addc.cc.u32 %6, %6, 0;\n\t"
         "addc.cc.u32 %7, %7, 0;\n\t"
         "addc.u32 %8, 0, 0;"
-        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(c)
+        : "+&r"(r[0]), "+&r"(r[1]), "+&r"(r[2]), "+&r"(r[3]), "+&r"(r[4]), "+&r"(r[5]), "+&r"(r[6]), "+&r"(r[7]), "=&r"(c)
         : "r"(lo), "r"(hi));
 #else
     u64 t = (u64)r[0] + lo;
@@ -142,7 +149,7 @@ SG_HD u32 sub8_small(u32* r, u32 lo, u32 hi) {
         "subc.cc.u32 %6, %6, 0;\n\t"
         "subc.cc.u32 %7, %7, 0;\n\t"
         "subc.u32 %8, 0, 0;"
-        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(c)
+        : "+&r"(r[0]), "+&r"(r[1]), "+&r"(r[2]), "+&r"(r[3]), "+&r"(r[4]), "+&r"(r[5]), "+&r"(r[6]), "+&r"(r[7]), "=&r"(c)
         : "r"(lo), "r"(hi));
     c &= 1u;
 #else
@@ -210,7 +217,7 @@ SG_HD u32 sub8_small(u32* r, u32 lo, u32 hi) {
 SG_HD u32 add1_c(u32* r, u32 v) {
     u32 c;
 #if SG_PTX
-    asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, 0, 0;" : "+r"(r[0]), "=r"(c) : "r"(v));
+    asm("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, 0, 0;" : "+&r"(r[0]), "=&r"(c) : "r"(v));
 #else
     u64 t = (u64)r[0] + v;
     r[0] = (u32)t;
@@ -221,7 +228,7 @@ SG_HD u32 add1_c(u32* r, u32 v) {
 SG_HD u32 sub1_b(u32* r, u32 v) {
     u32 c;
 #if SG_PTX
-    asm("sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, 0, 0;" : "+r"(r[0]), "=r"(c) : "r"(v));
+    asm("sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, 0, 0;" : "+&r"(r[0]), "=&r"(c) : "r"(v));
     c &= 1u;
 #else
     u64 t = (u64)r[0] - v;
@@ -235,7 +242,7 @@ SG_HD u32 add2_c(u32* r, u32 lo, u32 hi) {
     u32 c;
 #if SG_PTX
     asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, 0, 0;"
-        : "+r"(r[0]), "+r"(r[1]), "=r"(c)
+        : "+&r"(r[0]), "+&r"(r[1]), "=&r"(c)
         : "r"(lo), "r"(hi));
 #else
     u64 t = (u64)r[0] + lo;
@@ -250,7 +257,7 @@ SG_HD u32 sub2_b(u32* r, u32 lo, u32 hi) {
     u32 c;
 #if SG_PTX
     asm("sub.cc.u32 %0, %0, %3;\n\tsubc.cc.u32 %1, %1, %4;\n\tsubc.u32 %2, 0, 0;"
-        : "+r"(r[0]), "+r"(r[1]), "=r"(c)
+        : "+&r"(r[0]), "+&r"(r[1]), "=&r"(c)
         : "r"(lo), "r"(hi));
     c &= 1u;
 #else
@@ -268,7 +275,7 @@ SG_HD u32 add3_c(u32* r, u32 l0, u32 l1, u32 l2) {
     u32 c;
 #if SG_PTX
     asm("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %5;\n\taddc.cc.u32 %2, %2, %6;\n\taddc.u32 %3, 0, 0;"
-        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "=r"(c)
+        : "+&r"(r[0]), "+&r"(r[1]), "+&r"(r[2]), "=&r"(c)
         : "r"(l0), "r"(l1), "r"(l2));
 #else
     u64 t = (u64)r[0] + l0;
@@ -318,8 +325,8 @@ SG_HD u32 mad_row4(u32* acc, u32 x0, u32 x1, u32 x2, u32 x3, u32 b) {
         "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
         "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
         "addc.u32 %8, 0, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
-          "=r"(c)
+        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "+&r"(acc[4]), "+&r"(acc[5]), "+&r"(acc[6]), "+&r"(acc[7]),
+          "=&r"(c)
         : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
 #else
     const u32 x[4] = {x0, x1, x2, x3};
@@ -350,7 +357,7 @@ SG_HD u32 mad_row3(u32* acc, u32 x0, u32 x1, u32 x2, u32 b) {
         "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
         "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
         "addc.u32 %6, 0, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "=r"(c)
+        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "+&r"(acc[4]), "+&r"(acc[5]), "=&r"(c)
         : "r"(x0), "r"(x1), "r"(x2), "r"(b));
 #else
     const u32 x[3] = {x0, x1, x2};
@@ -379,7 +386,7 @@ SG_HD u32 mad_row2(u32* acc, u32 x0, u32 x1, u32 b) {
         "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
         "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
         "addc.u32 %4, 0, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(c)
+        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "=&r"(c)
         : "r"(x0), "r"(x1), "r"(b));
 #else
     const u32 x[2] = {x0, x1};
@@ -406,7 +413,7 @@ SG_HD u32 mad_row1(u32* acc, u32 x0, u32 b) {
     asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
         "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
         "addc.u32 %2, 0, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "=r"(c)
+        : "+&r"(acc[0]), "+&r"(acc[1]), "=&r"(c)
         : "r"(x0), "r"(b));
 #else
     u64 cur = ((u64)acc[1] << 32) | acc[0];
@@ -433,8 +440,8 @@ SG_HD void mad_row5(u32* acc, u32 x0, u32 x1, u32 x2, u32 x3, u32 b, u32 x4, u32
         "madc.hi.cc.u32 %7, %13, %14, %7;\n\t"
         "madc.lo.cc.u32 %8, %15, %16, 0;\n\t"
         "madc.hi.u32 %9, %15, %16, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]),
-          "=r"(acc[8]), "=r"(acc[9])
+        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "+&r"(acc[4]), "+&r"(acc[5]), "+&r"(acc[6]), "+&r"(acc[7]),
+          "=&r"(acc[8]), "=&r"(acc[9])
         : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b), "r"(x4), "r"(b2));
 #else
     u32 c = mad_row4(acc, x0, x1, x2, x3, b);
@@ -455,7 +462,7 @@ SG_HD void mad_row3c(u32* acc, u32 x0, u32 x1, u32 x2, u32 b) {
         "madc.hi.cc.u32 %5, %10, %11, %5;\n\t"
         "addc.cc.u32 %6, %6, 0;\n\t"
         "addc.u32 %7, %7, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+        : "+&r"(acc[0]), "+&r"(acc[1]), "+&r"(acc[2]), "+&r"(acc[3]), "+&r"(acc[4]), "+&r"(acc[5]), "+&r"(acc[6]), "+&r"(acc[7])
         : "r"(x0), "r"(x1), "r"(x2), "r"(b));
 #else
     u32 c = mad_row3(acc, x0, x1, x2, b);
@@ -468,7 +475,7 @@ SG_HD void mad_row3c(u32* acc, u32 x0, u32 x1, u32 x2, u32 b) {
 // (lo,hi) = x*b written to acc[0],acc[1] (no accumulate)
 SG_HD void mul_wide(u32* acc, u32 x, u32 b) {
 #if SG_PTX
-    asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=r"(acc[0]), "=r"(acc[1]) : "r"(x), "r"(b));
+    asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=&r"(acc[0]), "=&r"(acc[1]) : "r"(x), "r"(b));
 #else
     u64 p = (u64)x * b;
     acc[0] = (u32)p;
@@ -495,8 +502,8 @@ SG_HD void merge_even_odd(u32* r, const u32* e, const u32* o) {
         "addc.cc.u32 %12, %27, %42;\n\t"
         "addc.cc.u32 %13, %28, %43;\n\t"
         "addc.u32 %14, %29, %44;"
-        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(r[8]), "=&r"(r[9]),
+          "=&r"(r[10]), "=&r"(r[11]), "=&r"(r[12]), "=&r"(r[13]), "=&r"(r[14]), "=&r"(r[15])
         : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(e[8]), "r"(e[9]), "r"(e[10]),
           "r"(e[11]), "r"(e[12]), "r"(e[13]), "r"(e[14]), "r"(e[15]), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
           "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]),
@@ -591,7 +598,7 @@ SG_HD void mul4x4(u32* r, const u32* a, const u32* b) {
         "addc.cc.u32 %4, %11, %18;\n\t"
         "addc.cc.u32 %5, %12, %19;\n\t"
         "addc.u32 %6, %13, %20;"
-        : "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "=&r"(r[1]), "=&r"(r[2]), "=&r"(r[3]), "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7])
         : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(o[0]), "r"(o[1]), "r"(o[2]),
           "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]));
 #else
@@ -613,7 +620,7 @@ SG_HD u32 fold_halves(u32* s, const u32* x) {
         "addc.cc.u32 %2, %7, %11;\n\t"
         "addc.cc.u32 %3, %8, %12;\n\t"
         "addc.u32 %4, 0, 0;"
-        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(c)
+        : "=&r"(s[0]), "=&r"(s[1]), "=&r"(s[2]), "=&r"(s[3]), "=&r"(c)
         : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]));
 #else
     u64 t = 0;
@@ -653,7 +660,7 @@ SG_HD void mul8x8_kara(u32* r, const u32* a, const u32* b) {
         "addc.cc.u32 %2, %2, %11;\n\t"
         "addc.cc.u32 %3, %3, %12;\n\t"
         "addc.u32 %4, %4, 0;"
-        : "+r"(zm[4]), "+r"(zm[5]), "+r"(zm[6]), "+r"(zm[7]), "+r"(zm[8])
+        : "+&r"(zm[4]), "+&r"(zm[5]), "+&r"(zm[6]), "+&r"(zm[7]), "+&r"(zm[8])
         : "r"(ta[0]), "r"(ta[1]), "r"(ta[2]), "r"(ta[3]), "r"(tb[0]), "r"(tb[1]), "r"(tb[2]), "r"(tb[3]));
     // zm -= z0; zm -= z2   (the middle term a_lo b_hi + a_hi b_lo, below 2^257)
     asm("sub.cc.u32 %0, %0, %9;\n\t"
@@ -674,7 +681,7 @@ SG_HD void mul8x8_kara(u32* r, const u32* a, const u32* b) {
         "subc.cc.u32 %6, %6, %23;\n\t"
         "subc.cc.u32 %7, %7, %24;\n\t"
         "subc.u32 %8, %8, 0;"
-        : "+r"(zm[0]), "+r"(zm[1]), "+r"(zm[2]), "+r"(zm[3]), "+r"(zm[4]), "+r"(zm[5]), "+r"(zm[6]), "+r"(zm[7]), "+r"(zm[8])
+        : "+&r"(zm[0]), "+&r"(zm[1]), "+&r"(zm[2]), "+&r"(zm[3]), "+&r"(zm[4]), "+&r"(zm[5]), "+&r"(zm[6]), "+&r"(zm[7]), "+&r"(zm[8])
         : "r"(z0[0]), "r"(z0[1]), "r"(z0[2]), "r"(z0[3]), "r"(z0[4]), "r"(z0[5]), "r"(z0[6]), "r"(z0[7]), "r"(z2[0]),
           "r"(z2[1]), "r"(z2[2]), "r"(z2[3]), "r"(z2[4]), "r"(z2[5]), "r"(z2[6]), "r"(z2[7]));
     // r = z0 + zm 2^128 + z2 2^256
@@ -694,8 +701,8 @@ SG_HD void mul8x8_kara(u32* r, const u32* a, const u32* b) {
         "addc.cc.u32 %9, %30, 0;\n\t"
         "addc.cc.u32 %10, %31, 0;\n\t"
         "addc.u32 %11, %32, 0;"
-        : "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
-          "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "=&r"(r[4]), "=&r"(r[5]), "=&r"(r[6]), "=&r"(r[7]), "=&r"(r[8]), "=&r"(r[9]), "=&r"(r[10]), "=&r"(r[11]), "=&r"(r[12]),
+          "=&r"(r[13]), "=&r"(r[14]), "=&r"(r[15])
         : "r"(z0[4]), "r"(z0[5]), "r"(z0[6]), "r"(z0[7]), "r"(z2[0]), "r"(z2[1]), "r"(z2[2]), "r"(z2[3]), "r"(zm[0]),
           "r"(zm[1]), "r"(zm[2]), "r"(zm[3]), "r"(zm[4]), "r"(zm[5]), "r"(zm[6]), "r"(zm[7]), "r"(zm[8]), "r"(z2[4]),
           "r"(z2[5]), "r"(z2[6]), "r"(z2[7]));
@@ -753,8 +760,8 @@ SG_HD void mad_diag8(u32* r, const u32* a) {
         "madc.hi.cc.u32 %13, %22, %22, %13;\n\t"
         "madc.lo.cc.u32 %14, %23, %23, %14;\n\t"
         "madc.hi.u32 %15, %23, %23, %15;"
-        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-          "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+        : "+&r"(r[0]), "+&r"(r[1]), "+&r"(r[2]), "+&r"(r[3]), "+&r"(r[4]), "+&r"(r[5]), "+&r"(r[6]), "+&r"(r[7]), "+&r"(r[8]),
+          "+&r"(r[9]), "+&r"(r[10]), "+&r"(r[11]), "+&r"(r[12]), "+&r"(r[13]), "+&r"(r[14]), "+&r"(r[15])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
 #else
     u64 cy = 0;

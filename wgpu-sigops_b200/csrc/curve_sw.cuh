@@ -80,6 +80,8 @@ struct CurveK1T {
         const Fe beta = {SG_K1_BETA};
         F::mul(r, a, beta);
     }
+    // r = 3b * a = 21 a: the curve constant of the complete projective formulas (group.cuh)
+    static SG_HD void mul_bconst(Fe& r, const Fe& a) { F::mul_u32(r, a, 21u); }
 };
 typedef CurveK1T<FpK1> CurveK1;
 
@@ -107,6 +109,11 @@ struct CurveR1T {
         F::add(t, t, b);
     }
     static SG_HD void mul_beta(Fe& r, const Fe& a) { r = a; }
+    // r = b * a (Montgomery domain): the curve constant of the complete projective formulas for a = -3 (group.cuh)
+    static SG_HD void mul_bconst(Fe& r, const Fe& a) {
+        const Fe b = {SG_R1_B_MONT};
+        F::mul(r, a, b);
+    }
 };
 typedef CurveR1T<FpR1> CurveR1;
 

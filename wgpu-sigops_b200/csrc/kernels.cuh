@@ -176,8 +176,13 @@ SG_HD void unit_shape(int op, int& in_w, int& out_w) {
             out_w = 16;
             break;
         case SIGOPS_UNIT_K1_DOUBLE_MUL: case SIGOPS_UNIT_R1_DOUBLE_MUL:
+        case SIGOPS_UNIT_K1_GROUP_DOUBLE_MUL: case SIGOPS_UNIT_R1_GROUP_DOUBLE_MUL:
             in_w = 32;
             out_w = 17;
+            break;
+        case SIGOPS_UNIT_ED_GROUP_MULPT:
+            in_w = 24;
+            out_w = 16;
             break;
         case SIGOPS_UNIT_RAW_ADDSUB:
             in_w = 17;

@@ -29,6 +29,14 @@ int kl_gen_tables(cudaStream_t st, uint32_t* k1tab, uint32_t* r1tab, uint32_t* e
 int kl_unit(const KLaunch& l, int op, const uint32_t* in, size_t n, uint32_t* out, void* scratch, const uint32_t* k1g,
             const uint32_t* r1g, const uint32_t* edb);
 int kl_unit_setup(int* max_blocks_per_sm);
+// lane-group kernels (group.cuh): small batches, several cooperating warps per 32 signatures
+int kl_k1_group(const KLaunch& l, const void* sigs, const void* msgs, size_t n, void* out, uint8_t* status, const uint32_t* gtab);
+int kl_r1_group(const KLaunch& l, const void* sigs, const void* msgs, size_t n, void* out, uint8_t* status, const uint32_t* gtab);
+int kl_ed_group(const KLaunch& l, const void* sigs, const void* msgs, const void* pks, size_t n, uint8_t* valid, const uint32_t* btab);
+int kl_k1_group_setup(int* max_blocks_per_sm);
+int kl_r1_group_setup(int* max_blocks_per_sm);
+int kl_ed_group_setup(int* max_blocks_per_sm);
+int kl_unit_group(const KLaunch& l, int op, const uint32_t* in, size_t n, uint32_t* out, const uint32_t* k1g, const uint32_t* r1g);
 int kl_imad_peak(int kind, int grid, int block, cudaStream_t st, uint32_t* sink, int iters, uint32_t seed);
 
 }  // namespace sigops

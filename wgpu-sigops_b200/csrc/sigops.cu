@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "group.cuh"
 #include "launch.h"
 
 using namespace sigops;
@@ -113,6 +114,7 @@ struct Device {
     size_t h_out_cap = 0;
     const u32 *k1g = nullptr, *r1g = nullptr, *edb = nullptr;
     int grid_k1 = 0, grid_r1 = 0, grid_ed = 0, grid_edm = 0, grid_unit = 0;
+    int ggrid_k1 = 0, ggrid_r1 = 0, ggrid_ed = 0;  // resident blocks of the lane-group kernels
     float ms_h2d = 0, ms_kernel = 0, ms_d2h = 0;
     uint64_t last_call = 0;
     bool smem_tables = true;  // SIGOPS_SMEM_TABLES=0 leaves the fixed-base tables in L2
@@ -205,6 +207,33 @@ std::vector<std::unique_ptr<Device>>& pool() {
 }
 std::atomic<bool> g_inited{false};
 std::vector<int> g_ids;  // CUDA ordinals the pool was initialised with
+
+// Pinned allocations handed out by sigops_host_alloc (and owned by queue slots): known to be page-locked and mapped into
+// every device's address space (unified addressing), so small requests can be read and written by the kernels directly --
+// no driver query per call.
+std::mutex g_pin_mu;
+std::vector<std::pair<uintptr_t, size_t>> g_pinned;  // sorted by address
+void pinned_add(void* p, size_t bytes) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    auto e = std::make_pair((uintptr_t)p, bytes);
+    g_pinned.insert(std::upper_bound(g_pinned.begin(), g_pinned.end(), e), e);
+}
+void pinned_remove(void* p) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (size_t i = 0; i < g_pinned.size(); i++)
+        if (g_pinned[i].first == (uintptr_t)p) {
+            g_pinned.erase(g_pinned.begin() + i);
+            return;
+        }
+}
+bool pinned_ours(const void* p, size_t bytes) {
+    if (!p) return false;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    auto it = std::upper_bound(g_pinned.begin(), g_pinned.end(), std::make_pair((uintptr_t)p, (size_t)-1));
+    if (it == g_pinned.begin()) return false;
+    --it;
+    return (uintptr_t)p >= it->first && (uintptr_t)p + bytes <= it->first + it->second;
+}
 
 int ensure_buf(uint8_t** p, size_t* cap, size_t need) {
     if (need <= *cap) return 0;
@@ -309,6 +338,12 @@ int init_device(Device& d, int id, int index, int copy_threads) {
     d.grid_edm = std::max(per_sm2, 1) * d.sms;
     CK(kl_unit_setup(&per_sm));
     d.grid_unit = std::max(per_sm, 1) * d.sms;
+    CK(kl_k1_group_setup(&per_sm));
+    d.ggrid_k1 = std::max(per_sm, 1) * d.sms;
+    CK(kl_r1_group_setup(&per_sm));
+    d.ggrid_r1 = std::max(per_sm, 1) * d.sms;
+    CK(kl_ed_group_setup(&per_sm));
+    d.ggrid_ed = std::max(per_sm, 1) * d.sms;
     d.worker = std::thread([&d] { d.worker_main(); });
     for (int i = 0; i < copy_threads; i++) d.copiers.emplace_back([&d] { d.copier_main(); });
     return 0;
@@ -443,12 +478,43 @@ size_t tail_split(const Device& d, size_t n) {  // signatures in the main launch
     return n - tail;
 }
 
+// Small batches run on the lane-group kernels (group.cuh: several cooperating warps per 32 signatures, no device scratch):
+// below one block per SM the request's latency is one signature's dependent chain, which the group kernels cut roughly in
+// half.  SIGOPS_LANEGROUP=0 disables them, SIGOPS_FORCE_LANEGROUP=1 uses them for every size (tests),
+// SIGOPS_LANEGROUP_MAX=<n> moves the threshold.  Defaults from profiles/r02_latency_sweep.json: secp256k1 and ed25519 win
+// up to two 32-signature blocks per SM (9,472 signatures: 0.68 / 0.71 ms against 0.85 / 0.97), secp256r1 -- three-level
+// formulas, heavier field -- only while the request fits ~1,400 signatures (1.03 ms against 1.10).
+bool use_group_kernel(const Device& d, Op op, size_t n) {
+    if (env_int("SIGOPS_FORCE_LANEGROUP", 0) != 0) return true;
+    if (env_int("SIGOPS_LANEGROUP", 1) == 0) return false;
+    const int dflt = op == OP_R1 ? 1408 : 2 * d.sms * kGroupSigs;
+    const int lim = env_int("SIGOPS_LANEGROUP_MAX", dflt);
+    return n <= (size_t)std::max(lim, 0);
+}
+
+int launch_group(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_msgs, const uint8_t* d_pks, size_t n, uint8_t* d_out,
+                 uint8_t* d_status, cudaStream_t st) {
+    KLaunch l;
+    l.stream = st;
+    l.tpb = 0;
+    const int resident = op == OP_K1 ? d.ggrid_k1 : op == OP_R1 ? d.ggrid_r1 : d.ggrid_ed;
+    l.grid = (int)std::min<size_t>((n + kGroupSigs - 1) / kGroupSigs, (size_t)resident);
+    switch (op) {
+        case OP_K1: CK(kl_k1_group(l, d_sigs, d_msgs, n, d_out, d_status, d.k1g)); break;
+        case OP_R1: CK(kl_r1_group(l, d_sigs, d_msgs, n, d_out, d_status, d.r1g)); break;
+        case OP_ED: CK(kl_ed_group(l, d_sigs, d_msgs, d_pks, n, d_out, d.edb)); break;
+    }
+    if (!t_capturing) g_launches++;
+    return 0;
+}
+
 // The kernels index their per-thread scratch by global thread id: `scratch` must hold chunks x grid x tpb Q4 and must not
 // be shared by two launches that may run concurrently (launch_op orders the users of the per-device scratch with an event;
 // queue slots own theirs).
 int launch_op_scratch(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_msgs, const uint8_t* d_pks, size_t n,
                       uint8_t* d_out, uint8_t* d_status, Q4* scratch, cudaStream_t st) {
     if (n == 0) return 0;
+    if (use_group_kernel(d, op, n)) return launch_group(d, op, d_sigs, d_msgs, d_pks, n, d_out, d_status, st);
     const size_t main_n = tail_split(d, n);
     if (main_n < n) {
         const size_t os = op == OP_ED ? 1 : 64;
@@ -600,11 +666,71 @@ bool is_pageable(const void* p) {
     return a.type == cudaMemoryTypeUnregistered;
 }
 
+// Small requests (the sizes the lane-group kernels serve): one stream, no events between streams.  When every buffer came
+// from sigops_host_alloc the kernel reads the rows from and writes the results to the caller's pinned memory directly
+// (zero copy: ~100 B per signature each way over PCIe inside a ~0.45 ms kernel) -- the five small copies and the stream hops
+// of the pipelined path cost ~0.06 ms of a 0.49 ms request.  SIGOPS_ZERO_COPY=0 keeps the copies.
+int run_small(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n, uint8_t* out,
+              uint8_t* status, bool inject_fail) {
+    CK(cudaSetDevice(d.id));
+    const size_t out_stride = op == OP_ED ? 1 : 64;
+    const bool aligned = (((uintptr_t)sigs | (uintptr_t)msgs | (uintptr_t)pks | (uintptr_t)out) & 15u) == 0;
+    // measured (profiles/r02_latency_sweep.json): zero copy wins while the request fits one block per SM (4,736 signatures:
+    // 0.50 against 0.54 ms); at two blocks per SM the 16-byte host accesses of twice as many warps queue up on PCIe (secp256k1
+    // 0.87 against 0.64 ms), so above that the rows are copied
+    const bool zc = aligned && n <= (size_t)d.sms * kGroupSigs && env_int("SIGOPS_ZERO_COPY", 1) != 0 && pinned_ours(sigs, n * 64) && pinned_ours(msgs, n * 32) &&
+                    (op != OP_ED || pinned_ours(pks, n * 32)) && pinned_ours(out, n * out_stride) &&
+                    (op == OP_ED || !status || pinned_ours(status, n));
+    int rc = 0;
+    do {
+        rc = 1;
+        if (zc) {
+            if (cudaEventRecord(d.ev[1], d.stream) != cudaSuccess) break;
+            if (launch_op(d, op, sigs, msgs, pks, n, out, op == OP_ED ? nullptr : status, d.stream)) return 1;
+            if (cudaEventRecord(d.ev[2], d.stream) != cudaSuccess) break;
+        } else {
+            const size_t in_bytes = n * (op == OP_ED ? 128 : 96), out_bytes = op == OP_ED ? n : n * 65;
+            if (ensure_buf(&d.d_in, &d.in_cap, in_bytes + 64)) return 1;
+            if (ensure_buf(&d.d_out, &d.out_cap, out_bytes + 64)) return 1;
+            uint8_t *d_sigs = d.d_in, *d_msgs = d.d_in + n * 64, *d_pks = d.d_in + n * 96;
+            uint8_t* d_status = op == OP_ED ? nullptr : d.d_out + n * 64;
+            if (cudaMemcpyAsync(d_sigs, sigs, n * 64, cudaMemcpyHostToDevice, d.stream) != cudaSuccess) break;
+            if (cudaMemcpyAsync(d_msgs, msgs, n * 32, cudaMemcpyHostToDevice, d.stream) != cudaSuccess) break;
+            if (op == OP_ED && cudaMemcpyAsync(d_pks, pks, n * 32, cudaMemcpyHostToDevice, d.stream) != cudaSuccess) break;
+            if (cudaEventRecord(d.ev[1], d.stream) != cudaSuccess) break;
+            if (launch_op(d, op, d_sigs, d_msgs, d_pks, n, d.d_out, d_status, d.stream)) return 1;
+            if (cudaEventRecord(d.ev[2], d.stream) != cudaSuccess) break;
+            if (cudaMemcpyAsync(out, d.d_out, n * out_stride, cudaMemcpyDeviceToHost, d.stream) != cudaSuccess) break;
+            if (d_status && status && cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, d.stream) != cudaSuccess) break;
+        }
+        rc = 0;
+    } while (0);
+    const bool injected = !rc && inject_fail;  // fault injection: fail with the request in flight
+    const cudaError_t e = cudaStreamSynchronize(d.stream);  // nothing stays in flight, whatever happened
+    if (rc || injected || e != cudaSuccess) {
+        if (injected) {
+            char b[128];
+            snprintf(b, sizeof b, "injected failure on pool device %d (SIGOPS_FAIL_DEVICE)", d.index);
+            set_err(b);
+        } else {
+            set_err(std::string("small-request path failed: ") + cudaGetErrorString(e != cudaSuccess ? e : cudaGetLastError()));
+        }
+        cudaGetLastError();
+        return 1;
+    }
+    d.ms_h2d = 0;
+    d.ms_d2h = 0;
+    CK(cudaEventElapsedTime(&d.ms_kernel, d.ev[1], d.ev[2]));
+    return 0;
+}
+
 // Below this many signatures a pageable shard is copied directly (the driver stages small copies itself at no cost)
 constexpr size_t kMinStaged = 16384;
 
 int run_shard(Device& d, Op op, const uint8_t* sigs, const uint8_t* msgs, const uint8_t* pks, size_t n, uint8_t* out,
               uint8_t* status, bool inject_fail) {
+    if (use_group_kernel(d, op, n) && env_int("SIGOPS_SMALL_PATH", 1) != 0)
+        return run_small(d, op, sigs, msgs, pks, n, out, status, inject_fail);
     CK(cudaSetDevice(d.id));
     const size_t in_bytes = n * (op == OP_ED ? 128 : 96);
     const size_t out_stride = op == OP_ED ? 1 : 64;
@@ -932,6 +1058,11 @@ int queue_enqueue_tail(sigops_queue* q, QSlot& s, size_t n, cudaStream_t st) {
 // allocation, no synchronisation)
 int queue_enqueue(sigops_queue* q, QSlot& s, size_t n, cudaStream_t st) {
     const size_t cap = q->cap;
+    if (use_group_kernel(*s.dev, q->op, n) && n <= (size_t)s.dev->sms * kGroupSigs && env_int("SIGOPS_ZERO_COPY", 1) != 0) {
+        // small request: the lane-group kernel works on the slot's pinned arrays directly (zero copy)
+        uint8_t* h_status = q->op == OP_ED ? nullptr : s.h_out + cap * 64;
+        return launch_op_scratch(*s.dev, q->op, s.h_in, s.h_in + cap * 64, s.h_in + cap * 96, n, s.h_out, h_status, s.scratch, st);
+    }
     CK(cudaMemcpyAsync(s.d_in, s.h_in, n * 64, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(s.d_in + cap * 64, s.h_in + cap * 64, n * 32, cudaMemcpyHostToDevice, st));
     if (q->op == OP_ED) CK(cudaMemcpyAsync(s.d_in + cap * 96, s.h_in + cap * 96, n * 32, cudaMemcpyHostToDevice, st));
@@ -963,8 +1094,8 @@ int queue_alloc_slot(sigops_queue* q, QSlot& s) {
     CK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
     CK(cudaEventCreate(&s.t0));
     CK(cudaEventCreate(&s.t1));
-    CK(cudaHostAlloc((void**)&s.h_in, cap * 128, cudaHostAllocPortable));
-    CK(cudaHostAlloc((void**)&s.h_out, cap * 65, cudaHostAllocPortable));
+    CK(cudaHostAlloc((void**)&s.h_in, cap * 128, cudaHostAllocPortable | cudaHostAllocMapped));
+    CK(cudaHostAlloc((void**)&s.h_out, cap * 65, cudaHostAllocPortable | cudaHostAllocMapped));
     CK(cudaMalloc((void**)&s.d_in, cap * 128 + 64));
     CK(cudaMalloc((void**)&s.d_out, cap * 65 + 64));
     CK(cudaMalloc((void**)&s.scratch, chunks * threads * sizeof(Q4)));
@@ -1308,15 +1439,18 @@ uint64_t sigops_kernel_launches(void) { return g_launches.load(); }
 
 void* sigops_host_alloc(size_t bytes) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
         set_err("cudaHostAlloc failed");
         return nullptr;
     }
+    pinned_add(p, bytes ? bytes : 1);
     return p;
 }
 
 void sigops_host_free(void* p) {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    pinned_remove(p);
+    cudaFreeHost(p);
 }
 
 int sigops_precompute_bases(int curve, uint32_t log_limb_size, uint32_t* out, size_t* inout_len) {
@@ -1402,11 +1536,16 @@ int sigops_test_unit(int op, const uint32_t* in, size_t n, uint32_t* out) {
     KLaunch l;
     l.stream = d.stream;
     l.tpb = kBlock;
-    l.grid = (int)std::min<size_t>((n + kBlock - 1) / kBlock, (size_t)d.grid_unit);
-    if (d.scratch_used) CK(cudaStreamWaitEvent(d.stream, d.scratch_ev, 0));
-    CK(kl_unit(l, op, (const u32*)d.d_in, n, (u32*)d.d_out, d.scratch, d.k1g, d.r1g, d.edb));
-    CK(cudaEventRecord(d.scratch_ev, d.stream));
-    d.scratch_used = true;
+    if (op >= SIGOPS_UNIT_K1_GROUP_DOUBLE_MUL) {  // the lane-group twins: 32 items per block, no scratch
+        l.grid = (int)std::min<size_t>((n + kGroupSigs - 1) / kGroupSigs, (size_t)d.sms * 2);
+        CK(kl_unit_group(l, op, (const u32*)d.d_in, n, (u32*)d.d_out, d.k1g, d.r1g));
+    } else {
+        l.grid = (int)std::min<size_t>((n + kBlock - 1) / kBlock, (size_t)d.grid_unit);
+        if (d.scratch_used) CK(cudaStreamWaitEvent(d.stream, d.scratch_ev, 0));
+        CK(kl_unit(l, op, (const u32*)d.d_in, n, (u32*)d.d_out, d.scratch, d.k1g, d.r1g, d.edb));
+        CK(cudaEventRecord(d.scratch_ev, d.stream));
+        d.scratch_used = true;
+    }
     g_launches++;
     CK(cudaMemcpyAsync(out, d.d_out, n * out_w * 4, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaStreamSynchronize(d.stream));
@@ -1568,7 +1707,7 @@ int sigops_queue_submit(sigops_queue* q, int slot, size_t n) {
     CK(cudaEventRecord(s.t0, s.st));
     if (q->graphs) {
         CK(cudaGraphLaunch(s.exec, s.st));
-        g_launches += tail_split(*s.dev, n) < n ? 2 : 1;  // the fused kernel (twice when the tail is launched on its own)
+        g_launches += (!use_group_kernel(*s.dev, q->op, n) && tail_split(*s.dev, n) < n) ? 2 : 1;  // twice when the tail is launched on its own
         q->graph_launches++;
     } else if (queue_enqueue(q, s, n, s.st)) {
         return 1;
