@@ -484,7 +484,7 @@ SG_HD bool ed_verify_point(EdPoint& acc, const u32* sig_w, const u32* pk_w, cons
     for (int i = 63; i >= 0; i--) {
         phase_sync<kSync>();
         if (i != 63) {
-#pragma unroll 1
+            SG_PRAGMA_UNROLL(SG_DBL_UNROLL)
             for (int d = 0; d < 4; d++) {
 #if defined(SG_SYNC_DBL)
                 phase_sync<kSync>();

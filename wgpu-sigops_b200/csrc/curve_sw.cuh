@@ -432,6 +432,14 @@ SG_HD void phase_sync() {
 #endif
 }
 
+// The four doublings of a window: `#pragma unroll 1` keeps the loop body in the instruction cache but pays ~1 register move
+// per loop-carried limb and iteration; SG_DBL_UNROLL (1, 2 or 4) trades code size for those moves (profiles/r02_variants.md).
+#ifndef SG_DBL_UNROLL
+#define SG_DBL_UNROLL 1
+#endif
+#define SG_PRAGMA_(x) _Pragma(#x)
+#define SG_PRAGMA_UNROLL(n) SG_PRAGMA_(unroll n)
+
 template <class C, bool kSync>
 SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabRef& tab, const u32* gtab,
                          const u32* gtab_global) {
@@ -471,7 +479,7 @@ SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabR
         for (int i = 32; i >= 0; i--) {
             phase_sync<kSync>();
             if (i != 32) {
-#pragma unroll 1
+                SG_PRAGMA_UNROLL(SG_DBL_UNROLL)
                 for (int d = 0; d < 4; d++) {
 #if defined(SG_SYNC_DBL)
                     phase_sync<kSync>();
@@ -510,7 +518,7 @@ SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabR
         for (int i = 64; i >= 0; i--) {
             phase_sync<kSync>();
             if (i != 64) {
-#pragma unroll 1
+                SG_PRAGMA_UNROLL(SG_DBL_UNROLL)
                 for (int d = 0; d < 4; d++) {
 #if defined(SG_SYNC_DBL)
                     phase_sync<kSync>();

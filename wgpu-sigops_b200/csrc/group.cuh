@@ -487,17 +487,21 @@ SG_HD void sw_group_add_r(Fe& X, Fe& Y, Fe& Z, const TabRef& tab, int d, bool fl
     pj_madd_g<C>(X, Y, Z, x, y, d != 0, g);
 }
 
-template <class C>
-SG_HD void sw_group_add_g(Fe& X, Fe& Y, Fe& Z, const u32* gtab, int d, bool flip, const GroupCtx& g) {
-    typedef typename C::F F;
+// fixed-base entry |d| * G from the table in global memory (L2: ~700 cycles for a lone warp -- issued before the window's
+// doublings so that the latency is hidden behind them)
+SG_HD void sw_group_load_g(Fe& x, Fe& y, const u32* gtab, int d) {
     const int e = d == 0 ? 0 : (d < 0 ? -d : d) - 1;
-    Fe x, y;
     const Q4* q = reinterpret_cast<const Q4*>(gtab) + 4 * e;
     Q4 a = q[0], b = q[1], c = q[2], dd = q[3];
     x.v[0] = a.x; x.v[1] = a.y; x.v[2] = a.z; x.v[3] = a.w;
     x.v[4] = b.x; x.v[5] = b.y; x.v[6] = b.z; x.v[7] = b.w;
     y.v[0] = c.x; y.v[1] = c.y; y.v[2] = c.z; y.v[3] = c.w;
     y.v[4] = dd.x; y.v[5] = dd.y; y.v[6] = dd.z; y.v[7] = dd.w;
+}
+
+template <class C>
+SG_HD void sw_group_add_g(Fe& X, Fe& Y, Fe& Z, const Fe& x, Fe y, int d, bool flip, const GroupCtx& g) {
+    typedef typename C::F F;
     if ((d < 0) != flip) F::neg(y, y);
     pj_madd_g<C>(X, Y, Z, x, y, d != 0, g);
 }
@@ -514,6 +518,15 @@ SG_HD void sw_double_mul_g(Fe& X, Fe& Y, Fe& Z, const u32* kp, u32 flips, const 
         int gcount = 0;
 #pragma unroll 1
         for (int i = 32; i >= 0; i--) {
+            const bool gwin = i <= 30 && gcount == 0;
+            int d2 = 0, d3 = 0;
+            Fe gx2, gy2, gx3, gy3;
+            if (gwin) {
+                d2 = recode_digit<kGWin>(kp + 12, (i * 11) >> 5);
+                d3 = recode_digit<kGWin>(kp + 18, (i * 11) >> 5);
+                sw_group_load_g(gx2, gy2, gtab_global, d2);
+                sw_group_load_g(gx3, gy3, gtab_global + kGTabEntries * 16, d3);
+            }
             if (i != 32) {
 #pragma unroll 1
                 for (int d = 0; d < 4; d++) pj_dbl_g<C>(X, Y, Z, g);
@@ -522,11 +535,9 @@ SG_HD void sw_double_mul_g(Fe& X, Fe& Y, Fe& Z, const u32* kp, u32 flips, const 
             for (int s = 0; s < 2; s++)
                 sw_group_add_r<C>(X, Y, Z, tab, recode_digit<4>(kp + 6 * s, i), ((flips >> s) & 1u) != 0, s == 1, g);
             if (i <= 30) {
-                if (gcount == 0) {
-#pragma unroll 1
-                    for (int s = 2; s < 4; s++)
-                        sw_group_add_g<C>(X, Y, Z, s == 3 ? gtab_global + kGTabEntries * 16 : gtab_global,
-                                          recode_digit<kGWin>(kp + 6 * s, (i * 11) >> 5), ((flips >> s) & 1u) != 0, g);
+                if (gwin) {
+                    sw_group_add_g<C>(X, Y, Z, gx2, gy2, d2, ((flips >> 2) & 1u) != 0, g);
+                    sw_group_add_g<C>(X, Y, Z, gx3, gy3, d3, ((flips >> 3) & 1u) != 0, g);
                     gcount = 2;
                 } else {
                     gcount--;
@@ -537,14 +548,21 @@ SG_HD void sw_double_mul_g(Fe& X, Fe& Y, Fe& Z, const u32* kp, u32 flips, const 
         int gcount = 0;
 #pragma unroll 1
         for (int i = 64; i >= 0; i--) {
+            const bool gwin = i <= 63 && gcount == 0;
+            int dg = 0;
+            Fe gx, gy;
+            if (gwin) {
+                dg = recode_digit<kGWin>(kp + 10, (i * 43) >> 7);
+                sw_group_load_g(gx, gy, gtab_global, dg);
+            }
             if (i != 64) {
 #pragma unroll 1
                 for (int d = 0; d < 4; d++) pj_dbl_g<C>(X, Y, Z, g);
             }
             sw_group_add_r<C>(X, Y, Z, tab, recode_digit<4>(kp, i), false, false, g);
             if (i <= 63) {
-                if (gcount == 0) {
-                    sw_group_add_g<C>(X, Y, Z, gtab_global, recode_digit<kGWin>(kp + 10, (i * 43) >> 7), false, g);
+                if (gwin) {
+                    sw_group_add_g<C>(X, Y, Z, gx, gy, dg, false, g);
                     gcount = 2;
                 } else {
                     gcount--;
@@ -615,7 +633,53 @@ SG_HD bool sw_ecrecover_group(const u32* sig_w, const u32* msg_w, u32* out_w, u3
     SwParsed p;
     sw_parse<C>(p, sig_w, msg_w);
     constexpr int kKpWords = C::kGlv ? 24 : 20;
-    if (g.role == 0) {
+    if (C::kAIsZero) {
+        // secp256k1: the table of multiples of R is built WITHOUT y, in the shadow of the square-root chain.  With
+        // w = x^3 + 7 = y^2, the map (X, Y) -> (X / w, y Y / w^2) sends E'' : Y^2 = X^3 + 7 w^3 onto the curve, and
+        // P'' = (w x, w^2) on E'' goes to R = (x, y).  The Jacobian formulas for a = 0 do not involve b, so the multiples
+        // e P'' come out of the ordinary table code; w joins the shared inversion (Montgomery's trick), and when y arrives
+        // the y coordinates are scaled by it.  Role 0: y (254 squarings + 13 products); role 2: the table; role 1: scalars.
+        if (g.role == 0) {
+            u32 bad = p.ok ? 0u : 1u;
+            Fe x, y, t, y2;
+            F::from_plain(x, p.r);
+            C::rhs(t, x);
+            fe_sqrt_candidate((F*)0, y, t);
+            F::sqr(y2, y);
+            if (!F::eq(y2, t)) bad = 1u;  // x = r is not on the curve: invalid (the outputs are zeroed; the table is unused)
+            {
+                u32 yp[8];
+                F::to_plain(yp, y);
+                if ((yp[0] & 1u) != p.parity) F::neg(y, y);
+            }
+            g.put(14, y);
+            g.put_word(kKpWords + 1, bad);
+        } else if (g.role == 2) {
+            Fe x, w, xs, ys, c, inv;
+            F::from_plain(x, p.r);
+            C::rhs(w, x);
+            F::mul(xs, w, x);  // P'' = (w x, w^2)
+            F::sqr(ys, w);
+            c = w;
+            sw_table_park<C>(tab, xs, ys, c);
+            fe_inv((F*)0, inv, c);
+            sw_table_normalize<C>(tab, inv, w);  // leaves inv = w^-1
+            Fe om2;
+            F::sqr(om2, inv);
+#pragma unroll 1
+            for (int e = 0; e < kSwTabEntries; e++) {
+                Fe a;
+                tab_load_fe(a, tab, 4 * e);
+                F::mul(a, a, inv);  // x_e = X''_e / w
+                tab_store_fe(tab, 4 * e, a);
+                C::mul_beta(a, a);
+                tab_store_fe(tab, kSwTabChunks + 4 * e, a);
+                tab_load_fe(a, tab, 4 * e + 2);
+                F::mul(a, a, om2);  // y_e / y = Y''_e / w^2
+                tab_store_fe(tab, 4 * e + 2, a);
+            }
+        }
+    } else if (g.role == 0) {
         // lift x = r, table {1..8} R (affine), plus beta*x and -y per entry
         u32 bad = p.ok ? 0u : 1u;
         Fe x, y, t, y2;
@@ -635,7 +699,8 @@ SG_HD bool sw_ecrecover_group(const u32* sig_w, const u32* msg_w, u32* out_w, u3
         }
         sw_group_table<C>(tab, x, y);
         g.put_word(kKpWords + 1, bad);
-    } else if (g.role == 1) {
+    }
+    if (g.role == 1) {
         // r^-1 mod n, u1 = -z/r, u2 = s/r, GLV split, window recoding
         u32 ri[8], rim[8], u1[8], u2[8], kp[kKpWords];
         S::inv_plain(ri, p.r);
@@ -649,6 +714,21 @@ SG_HD bool sw_ecrecover_group(const u32* sig_w, const u32* msg_w, u32* out_w, u3
         g.put_word(kKpWords, flips);
     }
     g.sync();
+    if (C::kAIsZero) {
+        // y has arrived: entry e gets y_e = y (Y''_e / w^2) and -y_e, the entries spread over the roles
+        Fe y;
+        g.get(y, 14);
+#pragma unroll 1
+        for (int e = g.role; e < kSwTabEntries; e += kGroupRolesSw) {
+            Fe a;
+            tab_load_fe(a, tab, 4 * e + 2);
+            F::mul(a, a, y);
+            tab_store_fe(tab, 4 * e + 2, a);
+            F::neg(a, a);
+            tab_store_fe(tab, kSwTabChunks + 4 * e + 2, a);
+        }
+        g.sync();
+    }
     u32 kp[kKpWords];
 #pragma unroll
     for (int i = 0; i < kKpWords; i++) kp[i] = g.get_word(i);
@@ -950,6 +1030,16 @@ SG_HD u32 ed_verify_group(const u32* sig_w, const u32* msg_w, const u32* pk_w, c
     int gcount = 0;
 #pragma unroll 1
     for (int i = 63; i >= 0; i--) {
+        const bool bwin = gcount == 0;
+        int db = 0;
+        Fe bypx, bymx, bxy2d;
+        if (bwin) {  // the fixed-base entry comes from L2: issue the loads before the window's doublings
+            db = recode_digit<kGWin>(kp[1], (i * 43) >> 7);
+            const int e = db == 0 ? 0 : (db < 0 ? -db : db) - 1;
+            ed_load_fe_words(bypx, btab + 24 * e);
+            ed_load_fe_words(bymx, btab + 24 * e + 8);
+            ed_load_fe_words(bxy2d, btab + 24 * e + 16);
+        }
         if (i != 63) {
 #pragma unroll 1
             for (int d = 0; d < 4; d++) ed_dbl_g<FH>(acc, g);
@@ -964,14 +1054,8 @@ SG_HD u32 ed_verify_group(const u32* sig_w, const u32* msg_w, const u32* pk_w, c
             tab_load_fe(t2d, tab, 8 * e + 6);
             ed_add_g<FH>(acc, ypx, ymx, z2, t2d, true, d < 0, d != 0, g);
         }
-        if (gcount == 0) {
-            const int d = recode_digit<kGWin>(kp[1], (i * 43) >> 7);
-            const int e = d == 0 ? 0 : (d < 0 ? -d : d) - 1;
-            Fe ypx, ymx, xy2d;
-            ed_load_fe_words(ypx, btab + 24 * e);
-            ed_load_fe_words(ymx, btab + 24 * e + 8);
-            ed_load_fe_words(xy2d, btab + 24 * e + 16);
-            ed_add_g<FH>(acc, ypx, ymx, ypx, xy2d, false, d < 0, d != 0, g);
+        if (bwin) {
+            ed_add_g<FH>(acc, bypx, bymx, bypx, bxy2d, false, db < 0, db != 0, g);
             gcount = 2;
         } else {
             gcount--;

@@ -482,12 +482,13 @@ size_t tail_split(const Device& d, size_t n) {  // signatures in the main launch
 // below one block per SM the request's latency is one signature's dependent chain, which the group kernels cut roughly in
 // half.  SIGOPS_LANEGROUP=0 disables them, SIGOPS_FORCE_LANEGROUP=1 uses them for every size (tests),
 // SIGOPS_LANEGROUP_MAX=<n> moves the threshold.  Defaults from profiles/r02_latency_sweep.json: secp256k1 and ed25519 win
-// up to two 32-signature blocks per SM (9,472 signatures: 0.68 / 0.71 ms against 0.85 / 0.97), secp256r1 -- three-level
-// formulas, heavier field -- only while the request fits ~1,400 signatures (1.03 ms against 1.10).
+// while the request fits ONE 32-signature block per SM (4,736 signatures: 0.48 / 0.54 ms against 0.84 / 0.96) -- with two
+// blocks per SM the roles no longer have a scheduler to themselves and the one-thread-per-signature kernel is as fast
+// (0.85 ms); secp256r1 -- three-level formulas, heavier field -- only up to ~1,400 signatures (0.91 ms against 1.15).
 bool use_group_kernel(const Device& d, Op op, size_t n) {
     if (env_int("SIGOPS_FORCE_LANEGROUP", 0) != 0) return true;
     if (env_int("SIGOPS_LANEGROUP", 1) == 0) return false;
-    const int dflt = op == OP_R1 ? 1408 : 2 * d.sms * kGroupSigs;
+    const int dflt = op == OP_R1 ? 1408 : d.sms * kGroupSigs;
     const int lim = env_int("SIGOPS_LANEGROUP_MAX", dflt);
     return n <= (size_t)std::max(lim, 0);
 }
