@@ -4,7 +4,7 @@
 // (src/wgsl/bigint.wgsl:13-246, src/wgsl/ff.wgsl:122-138 `bigint_mul`,
 // src/wgsl/mont.wgsl:5-70 `mont_mul`) with full 32-bit limbs and PTX carry chains
 // (`add.cc/addc.cc`, `mad.lo.cc/madc.hi.cc`).  ptxas fuses each lo/hi pair into one
-// IMAD.WIDE.U32(.X) with the carry in a predicate register (see profiles/sass_*.txt).
+// IMAD.WIDE.U32(.X) with the carry in a predicate register (full listings: profiles/sass/r02_kern_*.sass.gz).
 //
 // Every output operand of a multi-instruction asm block is EARLY-CLOBBER ("=&r" / "+&r").  Without it the compiler may let
 // an output (in particular the tied input of a read-write accumulator) share a virtual register with another input that

@@ -82,6 +82,7 @@ struct CurveK1T {
     }
     // r = 3b * a = 21 a: the curve constant of the complete projective formulas (group.cuh)
     static SG_HD void mul_bconst(Fe& r, const Fe& a) { F::mul_u32(r, a, 21u); }
+    static SG_HD void mul_bconst3(Fe& r, const Fe& a) { F::mul_u32(r, a, 63u); }  // 9b
 };
 typedef CurveK1T<FpK1> CurveK1;
 
@@ -113,6 +114,12 @@ struct CurveR1T {
     static SG_HD void mul_bconst(Fe& r, const Fe& a) {
         const Fe b = {SG_R1_B_MONT};
         F::mul(r, a, b);
+    }
+    static SG_HD void mul_bconst3(Fe& r, const Fe& a) {  // unused by the a = -3 formulas; kept for the common interface
+        Fe t;
+        mul_bconst(t, a);
+        F::dbl(r, t);
+        F::add(r, r, t);
     }
 };
 typedef CurveR1T<FpR1> CurveR1;

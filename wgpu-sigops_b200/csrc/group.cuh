@@ -101,11 +101,10 @@ SG_HD void pj_dbl_g(Fe& X, Fe& Y, Fe& Z, const GroupCtx& g) {
                 break;
             case 2:
                 F::sqr(t, Z);
-                HC::mul_bconst(t, t);
-                g.put(3, t);  // t2 = 3b Z^2
-                F::dbl(u, t);
-                F::add(u, u, t);
-                g.put(4, u);  // 3 t2
+                HC::mul_bconst(u, t);
+                g.put(3, u);  // t2 = 3b Z^2
+                HC::mul_bconst3(u, t);
+                g.put(4, u);  // 3 t2 = 9b Z^2 (a second small product is shorter than a doubling plus an addition)
                 break;
             case 3:
                 F::mul(t, X, Y);
