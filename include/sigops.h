@@ -255,7 +255,8 @@ enum {
     SIGOPS_UNIT_K1_GROUP_DOUBLE_MUL = 40, /* in 32 (u1,u2,x,y)  out 17 : u1*G + u2*(x,y)                */
     SIGOPS_UNIT_R1_GROUP_DOUBLE_MUL = 41,
     SIGOPS_UNIT_ED_GROUP_MULPT = 42,      /* in 24 (k, x, y)    out 16 : k*(x,y) affine x,y             */
-    SIGOPS_UNIT_COUNT = 43
+    SIGOPS_UNIT_ED_FIXED_MUL = 43,        /* in 8 (s)           out 16 : s*B affine x,y, through the positional table only */
+    SIGOPS_UNIT_COUNT = 44
 };
 
 #ifdef __cplusplus

@@ -16,19 +16,43 @@
 
 using namespace sigops;
 
-// fixed-base tables, generated on the host with the same entry functions the device's gen_tables_kernel runs
-static std::vector<u32> k1_gtab, r1_gtab, ed_btab;
+// positional fixed-base tables (csrc/ptab.h), generated on the host with the same base / entry functions the device's
+// gen_ptab kernels run.  The window is narrow here (HOSTSIM_GWIN, default 7 bits: 37 windows of 64 entries) so that the
+// tables take a fraction of a second on one CPU core; the kernels take the width at run time, the GPU tests cover the
+// product's width; hostsim_set_gwin rebuilds them at another width (tests of the window arithmetic).
+static u32 g_gwin = 7;
+static std::vector<u32> k1_gtab_w, r1_gtab_w, ed_btab_w;
+static PTab k1_gtab, r1_gtab, ed_btab;
 static void ensure_tables() {
-    if (!k1_gtab.empty()) return;
-    k1_gtab.resize((size_t)2 * kGTabEntries * 16);
-    r1_gtab.resize((size_t)kGTabEntries * 16);
-    ed_btab.resize((size_t)kGTabEntries * 24);
-    for (u32 j = 0; j < (u32)kGTabEntries; j++) {
-        sw_gtab_entry<CurveK1>(&k1_gtab[(size_t)j * 16], j + 1, false, k1_g_host);
-        sw_gtab_entry<CurveK1>(&k1_gtab[((size_t)kGTabEntries + j) * 16], j + 1, true, k1_g_host);
-        sw_gtab_entry<CurveR1>(&r1_gtab[(size_t)j * 16], j + 1, false, r1_g_host);
-        ed_btab_entry(&ed_btab[(size_t)j * 24], j + 1, ed_b_niels_host);
+    if (!k1_gtab_w.empty()) return;
+    const u32 w = g_gwin, pos = ptab_positions(w);
+    const size_t per = (size_t)1 << (w - 1);
+    k1_gtab_w.resize(per * pos * 16);
+    r1_gtab_w.resize(per * pos * 16);
+    ed_btab_w.resize(per * pos * 24);
+    for (u32 j = 0; j < pos; j++) {
+        u32 bk[16], br[16], be[24];
+        sw_ptab_base<CurveK1>(bk, w * j);
+        sw_ptab_base<CurveR1>(br, w * j);
+        ed_ptab_base(be, w * j);
+        for (u32 m = 1; m <= per; m++) {
+            const size_t e = j * per + (m - 1);
+            sw_ptab_entry<CurveK1>(&k1_gtab_w[e * 16], m, w, bk);
+            sw_ptab_entry<CurveR1>(&r1_gtab_w[e * 16], m, w, br);
+            ed_ptab_entry(&ed_btab_w[e * 24], m, w, be);
+        }
     }
+    ptab_describe(k1_gtab, k1_gtab_w.data(), w);
+    ptab_describe(r1_gtab, r1_gtab_w.data(), w);
+    ptab_describe(ed_btab, ed_btab_w.data(), w);
+}
+
+extern "C" int hostsim_set_gwin(int w) {
+    if (w < (int)kPTabMinWin || w > 14) return 1;
+    g_gwin = (u32)w;
+    k1_gtab_w.clear();
+    ensure_tables();
+    return 0;
 }
 
 // ---- lane-group emulation: the roles of a signature are OS threads meeting at a pthread barrier (GroupCtx::sync) and
@@ -79,9 +103,9 @@ int hostsim_group_unit(int op, const uint32_t* in, size_t n, uint32_t* out) {
             for (int j = 0; j < 17; j++) r[j] = 0;
             bool writer;
             if (op == SIGOPS_UNIT_K1_GROUP_DOUBLE_MUL)
-                writer = unit_double_mul_g<CurveK1>(r, a, a + 8, a + 16, tab, k1_gtab.data(), g);
+                writer = unit_double_mul_g<CurveK1>(r, a, a + 8, a + 16, tab, k1_gtab, g);
             else if (op == SIGOPS_UNIT_R1_GROUP_DOUBLE_MUL)
-                writer = unit_double_mul_g<CurveR1>(r, a, a + 8, a + 16, tab, r1_gtab.data(), g);
+                writer = unit_double_mul_g<CurveR1>(r, a, a + 8, a + 16, tab, r1_gtab, g);
             else
                 writer = unit_ed_mulpt_g(r, a, tab, g);
             if (writer)
@@ -101,8 +125,8 @@ int hostsim_group_ecrecover(int curve, const uint8_t* sigs, const uint8_t* msgs,
             u32 sig_w[16], msg_w[8], out_w[16], st = 0;
             memcpy(sig_w, sigs + 64 * i, 64);
             memcpy(msg_w, msgs + 32 * i, 32);
-            const bool writer = curve == 0 ? sw_ecrecover_group<CurveK1>(sig_w, msg_w, out_w, &st, tab, k1_gtab.data(), g)
-                                           : sw_ecrecover_group<CurveR1>(sig_w, msg_w, out_w, &st, tab, r1_gtab.data(), g);
+            const bool writer = curve == 0 ? sw_ecrecover_group<CurveK1>(sig_w, msg_w, out_w, &st, tab, k1_gtab, g)
+                                           : sw_ecrecover_group<CurveR1>(sig_w, msg_w, out_w, &st, tab, r1_gtab, g);
             if (writer) {
                 memcpy(out + 64 * i, out_w, 64);
                 if (status) status[i] = (uint8_t)st;
@@ -123,7 +147,7 @@ int hostsim_group_ed25519_verify(const uint8_t* sigs, const uint8_t* msgs, const
             memcpy(sig_w, sigs + 64 * i, 64);
             memcpy(msg_w, msgs + 32 * i, 32);
             memcpy(pk_w, pks + 32 * i, 32);
-            const u32 v = ed_verify_group(sig_w, msg_w, pk_w, tab, ed_btab.data(), g);
+            const u32 v = ed_verify_group(sig_w, msg_w, pk_w, tab, ed_btab, g);
             if (role == 0) valid[i] = (uint8_t)v;
             g.sync();
         }
@@ -132,7 +156,7 @@ int hostsim_group_ed25519_verify(const uint8_t* sigs, const uint8_t* msgs, const
 }
 
 int hostsim_unit(int op, const uint32_t* in, size_t n, uint32_t* out) {
-    if (op >= SIGOPS_UNIT_K1_GROUP_DOUBLE_MUL) return hostsim_group_unit(op, in, n, out);
+    if (op >= SIGOPS_UNIT_K1_GROUP_DOUBLE_MUL && op <= SIGOPS_UNIT_ED_GROUP_MULPT) return hostsim_group_unit(op, in, n, out);
     ensure_tables();
     int in_w, out_w;
     unit_shape(op, in_w, out_w);
@@ -142,7 +166,7 @@ int hostsim_unit(int op, const uint32_t* in, size_t n, uint32_t* out) {
         u32 a[32], r[17];
         for (int j = 0; j < 32; j++) a[j] = j < in_w ? in[i * in_w + j] : 0u;
         for (int j = 0; j < 17; j++) r[j] = 0;
-        unit_dispatch(op, r, a, tab, k1_gtab.data(), r1_gtab.data(), ed_btab.data());
+        unit_dispatch(op, r, a, tab, k1_gtab, r1_gtab, ed_btab);
         for (int j = 0; j < out_w; j++) out[i * out_w + j] = r[j];
     }
     return 0;
@@ -185,9 +209,9 @@ int hostsim_ecrecover(int curve, const uint8_t* sigs, const uint8_t* msgs, size_
         const int B = (int)std::min<size_t>((size_t)batch, n - i);
         i += (size_t)B;
         if (curve == 0)
-            sw_ecrecover_batch<CurveK1, false>(B, io, tab, k1_gtab.data(), k1_gtab.data());
+            sw_ecrecover_batch<CurveK1, false>(B, io, tab, k1_gtab);
         else
-            sw_ecrecover_batch<CurveR1, false>(B, io, tab, r1_gtab.data(), r1_gtab.data());
+            sw_ecrecover_batch<CurveR1, false>(B, io, tab, r1_gtab);
         batch = batch == 1 ? kSwBatch : batch - 1;  // 8, 7, ..., 1, 8, ...: every batch size gets exercised
     }
     return 0;
@@ -220,7 +244,7 @@ int hostsim_ed25519_verify(const uint8_t* sigs, const uint8_t* msgs, const uint8
         io.first = i;
         const int B = (int)std::min<size_t>((size_t)batch, n - i);
         i += (size_t)B;
-        ed_verify_batch<false>(B, io, tab, ed_btab.data());
+        ed_verify_batch<false>(B, io, tab, ed_btab);
         batch = batch == 1 ? kEdBatch : batch - 1;
     }
     return 0;
@@ -236,7 +260,7 @@ int hostsim_ed25519_verify_msgs(const uint8_t* sigs, const uint8_t* msg_bytes, c
         memcpy(sig_w, sigs + 64 * i, 64);
         memcpy(pk_w, pks + 32 * i, 32);
         valid[i] = (uint8_t)ed_verify_msg<false>(sig_w, msg_bytes + off[i], (size_t)(off[i + 1] - off[i]), pk_w, strict != 0, tab,
-                                                 ed_btab.data());
+                                                 ed_btab);
     }
     return 0;
 }

@@ -40,6 +40,7 @@ def load_hostsim():
     lib.hostsim_group_unit.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     lib.hostsim_group_ecrecover.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     lib.hostsim_group_ed25519_verify.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p]
+    lib.hostsim_set_gwin.argtypes = [ctypes.c_int]
     return lib
 
 

@@ -46,3 +46,14 @@ def test_glv(gpu_units):
 
 def test_curves(gpu_units):
     uc.check_curves(gpu_units, n=40)
+
+
+def test_positional_fixed_base_tables(gpu_units):
+    """u1*G and s*B through the device-generated positional tables (csrc/ptab.h) at the library's window width: edge
+    scalars of that width (every window at an extreme digit, bits on both sides of every window boundary) and random ones."""
+    import os
+
+    w = int(os.environ.get("SIGOPS_GWIN", "20"))
+    uc.check_fixed_base(gpu_units, w)
+    if w != 20:
+        uc.check_fixed_base(gpu_units, 20)  # scalars built for another width are ordinary inputs: one more sample

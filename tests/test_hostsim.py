@@ -125,3 +125,17 @@ def test_lanegroup_ecrecover_and_verify_logic():
     got = np.zeros(600, dtype=np.uint8)
     lib.hostsim_group_ed25519_verify(sigs.tobytes(), msgs.tobytes(), pks.tobytes(), 600, got.ctypes.data)
     assert not (got != exp).any()
+
+
+def test_positional_fixed_base_tables(sim_units):
+    """The fixed-base halves (u1*G, s*B) through positional tables of several window widths: the digit arithmetic (offset
+    recoding, carries into the top window, the most negative digit) is width-dependent, the kernels take the width at run
+    time, and the GPU library runs a width the CPU cannot generate in reasonable time."""
+    lib = load_hostsim()
+    try:
+        for w in (4, 5, 9, 12):
+            assert lib.hostsim_set_gwin(w) == 0
+            uc.check_fixed_base(sim_units, w)
+    finally:
+        assert lib.hostsim_set_gwin(7) == 0
+    uc.check_fixed_base(sim_units, 7)

@@ -264,6 +264,50 @@ def check_curves(U, n=12, seed=7):
         assert (from_words(w[:8]), from_words(w[8:16])) == e
 
 
+def fixed_base_scalars(order, w, rng, nrand=6):
+    """Scalars that stress the positional table's signed windows of width w: zero, one, the order's neighbours, all-ones,
+    every window at its most negative / most positive digit, single bits on both sides of every window boundary."""
+    pos = 256 // w + 1
+    vals = [0, 1, 2, order - 1, order - 2, (order + 1) // 2, 2**256 - 1, 2**255, 2**252, 2**128]
+    half = 1 << (w - 1)
+    vals.append(sum(half << (w * j) for j in range(pos)) % 2**256)            # digits -2^(w-1) (after the offset: 0)
+    vals.append(sum((half - 1) << (w * j) for j in range(pos)) % 2**256)      # digits 2^(w-1) - 1
+    vals.append(sum((half + 1) << (w * j) for j in range(pos)) % 2**256)      # digits -(2^(w-1) - 1) with carries
+    for j in (1, 2, pos // 2, pos - 2, pos - 1):
+        for b in (w * j - 1, w * j):
+            if 0 <= b < 256:
+                vals.append(1 << b)
+                vals.append((1 << b) - 1)
+    vals += [rng.getrandbits(256) for _ in range(nrand)]
+    return vals
+
+
+def check_fixed_base(U, w, seed=23):
+    """u1*G (secp256k1, secp256r1: DOUBLE_MUL with u2 = 0 and with u2 = 1) and s*B (ED_FIXED_MUL) through the positional
+    fixed-base tables, against plain double-and-add of the oracle.  `w` is the window width the tables were built with (it
+    only selects the edge scalars)."""
+    rng = random.Random(seed)
+    for name, c in (("K1", o.K1), ("R1", o.R1)):
+        G = (c.gx, c.gy)
+        P = o.sw_mul(c, 0xC0FFEE, G)
+        items, exps = [], []
+        for k in fixed_base_scalars(c.n, w, rng):
+            k %= c.n
+            for u2 in (0, 1):
+                items.append((k, u2, P[0], P[1]))
+                exps.append(o.sw_add(c, o.sw_mul(c, k, G), o.sw_mul(c, u2, P)))
+        for ops in (name + "_DOUBLE_MUL", name + "_GROUP_DOUBLE_MUL"):
+            for e, wd in zip(exps, U.run(ops, items)):
+                if e is None:
+                    assert wd[16] == 1
+                else:
+                    assert wd[16] == 0 and (from_words(wd[:8]), from_words(wd[8:16])) == e, (ops, w)
+    ks = fixed_base_scalars(o.ED_L, w, rng)
+    out = U.run("ED_FIXED_MUL", [(k,) for k in ks])
+    for k, wd in zip(ks, out):
+        assert (from_words(wd[:8]), from_words(wd[8:16])) == _affine_ed(o.ed_mul(k, o.ED_B)), (k, w)
+
+
 def check_group_curves(U, n=12, seed=17):
     """The lane-group kernels' double-scalar multiplication (complete projective formulas, cooperating roles) and the
     four-role Edwards ladder through their unit shims: the reference's Strauss-Shamir corner case, R = +-G, a sum that is the

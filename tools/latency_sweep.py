@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """p50 latency of the blocking C-ABI calls for small batches (pinned buffers), lane-group kernels on / off.
-   python tools/latency_sweep.py [reps]            (under gpurun)"""
+   python tools/latency_sweep.py [reps]            (under gpurun)
+   LAT_SIZES=21,1024  LAT_MODES=group,thread  LAT_OUT=<file>  narrow the sweep."""
 import ctypes
 import json
 import os
@@ -34,10 +35,14 @@ def main():
     po, vo = pin(np.zeros(nmax * 64, np.uint8))
     pt, vt = pin(np.zeros(nmax, np.uint8))
     res = {}
+    sizes = [int(x) for x in os.environ.get("LAT_SIZES", "21,256,1024,1365,2048,4736,9472,16384").split(",")]
+    modes = os.environ.get("LAT_MODES", "group,thread,group_forced").split(",")
     for mode, env in (("group", {}), ("thread", {"SIGOPS_LANEGROUP": "0"}), ("group_forced", {"SIGOPS_FORCE_LANEGROUP": "1"})):
+        if mode not in modes:
+            continue
         for k, v in env.items():
             os.environ[k] = v
-        for n in (21, 256, 1024, 1365, 2048, 4736, 9472, 16384):
+        for n in sizes:
             row = {}
             for c in ("k1", "r1", "ed"):
                 def call():
@@ -67,7 +72,7 @@ def main():
             print(mode, n, row, flush=True)
         for k in env:
             del os.environ[k]
-    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "latency_sweep.json"), "w"), indent=1)
+    json.dump(res, open(os.environ.get("LAT_OUT", os.path.join(ROOT, "gpurun_out", "latency_sweep.json")), "w"), indent=1)
 
 
 if __name__ == "__main__":

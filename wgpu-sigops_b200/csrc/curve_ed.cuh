@@ -304,31 +304,47 @@ SG_HD void ed_load_fe_words(Fe& a, const u32* w) {
     a.v[4] = hi.x; a.v[5] = hi.y; a.v[6] = hi.z; a.v[7] = hi.w;
 }
 
-template <class FE>
-SG_HD void ed_add_from_btab(EdPoint& acc, const u32* btab, int d, bool need_t) {
-    if (d == 0) return;
-    int e = (d < 0 ? -d : d) - 1;
-    Fe ypx, ymx, xy2d;
-    ed_load_fe_words(ypx, btab + 24 * e);
-    ed_load_fe_words(ymx, btab + 24 * e + 8);
-    ed_load_fe_words(xy2d, btab + 24 * e + 16);
-    ed_add_niels<FE>(acc, ypx, ymx, xy2d, d < 0, need_t);
+// ---- the fixed-base half s*B from the positional table (ptab.h): affine Niels triples (y+x, y-x, 2d*x*y), 24 words ----
+SG_HD void ed_ptab_load(Fe& ypx, Fe& ymx, Fe& xy2d, const PTab& t, u32 j, int d) {
+    const u32* e = t.base + ptab_offset(t, j, d, 24);
+    ed_load_fe_words(ypx, e);
+    ed_load_fe_words(ymx, e + 8);
+    ed_load_fe_words(xy2d, e + 16);
 }
 
-// Entry j (1-based) of the fixed-base table: j*B as an affine Niels triple (y+x, y-x, 2d*x*y), 24 words.
-// b_niels: the base point's own Niels triple.  Runs once per entry at init.
-SG_HD void ed_btab_entry(u32* out24, u32 j, const u32* b_niels) {
+// acc = sum_j d_j * T[j] = 2^-252 * s * B in extended coordinates (T valid); the next entry is loaded before the current
+// addition (one 96-byte gather per lane)
+template <class FE>
+SG_HD void ed_ptab_sum(EdPoint& acc, const u32* s8, const PTab& t) {
+    ed_set_identity(acc);
+    u32 kp[9];
+    ptab_recode(kp, s8, t);
+    int d = ptab_pop_digit(kp, t.w);
     Fe ypx, ymx, xy2d;
-    copy8(ypx.v, b_niels);
-    copy8(ymx.v, b_niels + 8);
-    copy8(xy2d.v, b_niels + 16);
-    EdPoint P;
-    ed_set_identity(P);
+    ed_ptab_load(ypx, ymx, xy2d, t, 0, d);
 #pragma unroll 1
-    for (int b = kGWin - 1; b >= 0; b--) {
-        ed_dbl<FE>(P, true);
-        if ((j >> b) & 1u) ed_add_niels<FE>(P, ypx, ymx, xy2d, false, true);
+    for (u32 j = 0; j < t.pos; j++) {
+        Fe a = ypx, b = ymx, c = xy2d;
+        int dn = 0;
+        if (j + 1 < t.pos) {
+            dn = ptab_pop_digit(kp, t.w);
+            ed_ptab_load(a, b, c, t, j + 1, dn);
+        }
+        if (d != 0) ed_add_niels<FE>(acc, ypx, ymx, xy2d, d < 0, true);
+        ypx = a;
+        ymx = b;
+        xy2d = c;
+        d = dn;
     }
+}
+
+#if SG_PTX
+SG_HD const u32* ed_pt0_niels() { return ed_pt0_niels_dev; }
+#else
+SG_HD const u32* ed_pt0_niels() { return ed_pt0_niels_host; }
+#endif
+
+SG_HD void ed_ptab_write(u32* out24, const EdPoint& P) {
     const Fe d2 = {SG_ED_D2};
     Fe zi, x, y, t;
     fe_inv((FE*)0, zi, P.Z);
@@ -344,6 +360,36 @@ SG_HD void ed_btab_entry(u32* out24, u32 j, const u32* b_niels) {
     FE::mul(t, t, d2);
     FE::normalize(t, t);
     copy8(out24 + 16, t.v);
+}
+
+// Window base B_j = 2^(w j) * 2^-252 * B as an affine Niels triple: `ndbl` doublings of the baked seed
+SG_HD void ed_ptab_base(u32* out24, u32 ndbl) {
+    Fe ypx, ymx, xy2d;
+    copy8(ypx.v, ed_pt0_niels());
+    copy8(ymx.v, ed_pt0_niels() + 8);
+    copy8(xy2d.v, ed_pt0_niels() + 16);
+    EdPoint P;
+    ed_set_identity(P);
+    ed_add_niels<FE>(P, ypx, ymx, xy2d, false, true);
+#pragma unroll 1
+    for (u32 i = 0; i < ndbl; i++) ed_dbl<FE>(P, false);
+    ed_ptab_write(out24, P);
+}
+
+// Entry m * B_j (1 <= m <= 2^(w-1)) by double-and-add over the w bits of m.  Runs once per entry at init.
+SG_HD void ed_ptab_entry(u32* out24, u32 m, u32 w, const u32* base24) {
+    Fe ypx, ymx, xy2d;
+    copy8(ypx.v, base24);
+    copy8(ymx.v, base24 + 8);
+    copy8(xy2d.v, base24 + 16);
+    EdPoint P;
+    ed_set_identity(P);
+#pragma unroll 1
+    for (int b = (int)w - 1; b >= 0; b--) {
+        ed_dbl<FE>(P, true);
+        if ((m >> b) & 1u) ed_add_niels<FE>(P, ypx, ymx, xy2d, false, true);
+    }
+    ed_ptab_write(out24, P);
 }
 
 // sqrt_ratio_i (curve25519-dalek; src/wgsl/ed25519_utils.wgsl:42-88): returns whether u/v is a square and the
@@ -406,7 +452,7 @@ SG_HD bool ed_is_small_order(const Fe& x, const Fe& y) {
 // neither A nor R may have small order.  Returns 1 when the signature verifies, else 0.
 // Part 1: everything up to the projective point R' = [s]B + [k](-A).  Returns whether the inputs were acceptable so far.
 template <bool kSync, bool kStrict>
-SG_HD bool ed_verify_point(EdPoint& acc, const u32* sig_w, const u32* pk_w, const u32* dig, const TabRef& tab, const u32* btab) {
+SG_HD bool ed_verify_point(EdPoint& acc, const u32* sig_w, const u32* pk_w, const u32* dig, const TabRef& tab, const PTab& btab) {
     typedef Sc<ModEdL> S;
 #if !defined(SG_NO_HOT_INLINE)
     typedef Inl<Fp25519> FH;  // products inlined: one doubling, one cached-addition and one Niels-addition site
@@ -470,16 +516,14 @@ SG_HD bool ed_verify_point(EdPoint& acc, const u32* sig_w, const u32* pk_w, cons
         ed_dbl<FE>(T, true);
         ed_tab_store(tab, 7, T);
     }
-    // R' = [s]B + [k](-A): 64 signed 4-bit windows for k, 32 signed 8-bit windows for s, 252 shared doublings
-    u32 kp[2][10];
-    copy8(kp[0], k);
-    copy8(kp[1], sig_w + 8);
-    kp[0][8] = kp[0][9] = 0;
-    kp[1][8] = kp[1][9] = 0;
-    recode_offset<8, 4, 64>(kp[0]);      // k < L < 2^253: k + C < 2^256
-    recode_offset<9, kGWin, 22>(kp[1]);  // s < L: s + C < 2^264
-    ed_set_identity(acc);
-    int gcount = 0;  // B windows sit on every third k window: i = 63, 60, ..., 0  <->  window i / 3
+    // R' = [s]B + [k](-A): the accumulator starts as 2^-252 [s]B from the positional table, then 64 signed 4-bit windows
+    // for k over 252 doublings
+    static_assert(kPTabShiftEd == 63 * 4, "the table's scale follows the loop's doublings");
+    u32 kp[10];
+    copy8(kp, k);
+    kp[8] = kp[9] = 0;
+    recode_offset<8, 4, 64>(kp);  // k < L < 2^253: k + C < 2^256
+    ed_ptab_sum<FE>(acc, sig_w + 8, btab);
 #pragma unroll 1
     for (int i = 63; i >= 0; i--) {
         phase_sync<kSync>();
@@ -492,13 +536,7 @@ SG_HD bool ed_verify_point(EdPoint& acc, const u32* sig_w, const u32* pk_w, cons
                 ed_dbl<FH>(acc, d == 3);
             }
         }
-        ed_add_from_table<FHA>(acc, tab, recode_digit<4>(kp[0], i), true);
-        if (gcount == 0) {
-            ed_add_from_btab<FHA>(acc, btab, recode_digit<kGWin>(kp[1], (i * 43) >> 7 /* i / 3 */), true);
-            gcount = 2;
-        } else {
-            gcount--;
-        }
+        ed_add_from_table<FHA>(acc, tab, recode_digit<4>(kp, i), true);
     }
     // a key that is not a curve point can drive Z to zero: keep the inversion chain invertible (the verdict is 0 anyway)
     if (!ok || FE::is_zero(acc.Z)) {
@@ -521,7 +559,7 @@ SG_HD u32 ed_verify_finish(const EdPoint& acc, const Fe& zi, const u32* sig_w, b
 
 // One signature given the challenge digest (variable-length / strict entry point, unit shims)
 template <bool kSync, bool kStrict>
-SG_HD u32 ed_verify_core(const u32* sig_w, const u32* pk_w, const u32* dig, const TabRef& tab, const u32* btab) {
+SG_HD u32 ed_verify_core(const u32* sig_w, const u32* pk_w, const u32* dig, const TabRef& tab, const PTab& btab) {
     EdPoint acc;
     const bool ok = ed_verify_point<kSync, kStrict>(acc, sig_w, pk_w, dig, tab, btab);
     phase_sync<kSync>();
@@ -535,11 +573,11 @@ SG_HD u32 ed_verify_core(const u32* sig_w, const u32* pk_w, const u32* dig, cons
 // IO:  io.load(j, sig_w[16], msg_w[8], pk_w[8])  and  io.store(j, verdict).
 // Scratch in 16-byte chunks: the table {1..8}(-A) (kEdTabChunks, reused by every signature of the batch), then per
 // signature X, Y, Z (6) and the Z-chain slot (2).
-static constexpr int kEdBatch = 8;
+static constexpr int kEdBatch = SG_BATCH;
 static constexpr int kEdBatchChunks = kEdTabChunks + 8 * kEdBatch;
 
 template <bool kSync, class IO>
-SG_HD void ed_verify_batch(int B, IO& io, const TabRef& scratch, const u32* btab) {
+SG_HD void ed_verify_batch(int B, IO& io, const TabRef& scratch, const PTab& btab) {
     const int kQ = kEdTabChunks, kZP = kQ + 6 * kEdBatch;
     u32 sig_w[16], msg_w[8], pk_w[8];
     u32 good = 0;
@@ -585,7 +623,7 @@ SG_HD void ed_verify_batch(int B, IO& io, const TabRef& scratch, const u32* btab
 
 // The reference's fixed-size case: 32-byte message, non-strict (src/ed25519_eddsa.rs:67-73).
 template <bool kSync>
-SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, const TabRef& tab, const u32* btab) {
+SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, const TabRef& tab, const PTab& btab) {
     u32 pre[24], dig[16];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -600,7 +638,7 @@ SG_HD u32 ed_verify_one(const u32* sig_w, const u32* msg_w, const u32* pk_w, con
 // Variable-length message, optionally strict (fuel_crypto::ed25519::verify = dalek `verify_strict`).
 template <bool kSync>
 SG_HD u32 ed_verify_msg(const u32* sig_w, const uint8_t* msg, size_t len, const u32* pk_w, bool strict, const TabRef& tab,
-                        const u32* btab) {
+                        const PTab& btab) {
     u32 dig[16];
     sha512_ram(dig, sig_w, pk_w, msg, len);
     return strict ? ed_verify_core<kSync, true>(sig_w, pk_w, dig, tab, btab)

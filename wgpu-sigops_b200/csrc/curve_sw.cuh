@@ -83,6 +83,14 @@ struct CurveK1T {
     // r = 3b * a = 21 a: the curve constant of the complete projective formulas (group.cuh)
     static SG_HD void mul_bconst(Fe& r, const Fe& a) { F::mul_u32(r, a, 21u); }
     static SG_HD void mul_bconst3(Fe& r, const Fe& a) { F::mul_u32(r, a, 63u); }  // 9b
+    // the generator and the seed 2^-128 G of the positional table (ptab.h), affine x || y in the internal form
+#if SG_PTX
+    static SG_HD const u32* gen() { return k1_g_dev; }
+    static SG_HD const u32* pt0() { return k1_pt0_dev; }
+#else
+    static SG_HD const u32* gen() { return k1_g_host; }
+    static SG_HD const u32* pt0() { return k1_pt0_host; }
+#endif
 };
 typedef CurveK1T<FpK1> CurveK1;
 
@@ -121,6 +129,13 @@ struct CurveR1T {
         F::dbl(r, t);
         F::add(r, r, t);
     }
+#if SG_PTX
+    static SG_HD const u32* gen() { return r1_g_dev; }
+    static SG_HD const u32* pt0() { return r1_pt0_dev; }
+#else
+    static SG_HD const u32* gen() { return r1_g_host; }
+    static SG_HD const u32* pt0() { return r1_pt0_host; }
+#endif
 };
 typedef CurveR1T<FpR1> CurveR1;
 
@@ -268,12 +283,6 @@ static constexpr int kSwTabEntries = 8;
 static constexpr int kSwTabChunks = 60;
 static constexpr int kSwTabZ = 32, kSwTabC = 46;
 
-// fixed-base tables: j*G for j = 1..2^(kGWin-1), affine (x, y) in the field's internal form, 16 words per entry;
-// secp256k1 carries a second table for lambda*G = (beta*x, y) right behind the first one.  Generated once per device at
-// init (gen_tables_kernel); 12-bit signed windows: 11 additions per 128-bit half scalar, 22 per 256-bit scalar.
-static constexpr int kGWin = 12;
-static constexpr int kGTabEntries = 1 << (kGWin - 1);
-
 // Step 1 of the table: the Jacobian multiples 2R..8R (X, Y parked in their final slots, Z in the temp area) and the
 // running product of their Z (prefix products stored per entry).  `c` is the running product on entry and exit, so the
 // chain can span several signatures' tables (one shared inversion for all of them).
@@ -377,40 +386,89 @@ SG_HD void sw_add_from_table(JacPoint& acc, const TabRef& tab, int d, bool flip,
     jac_madd<C>(acc, x, y);
 }
 
-// acc += sign(d) * |d| * G from a fixed-base table in global memory (entry j-1 = j*G: x at words [16(j-1), +8), y next)
-template <class C>
-SG_HD void sw_add_from_gtab(JacPoint& acc, const u32* gtab, int d, bool flip) {
-    typedef typename C::F F;
-    if (d == 0) return;
-    int e = (d < 0 ? -d : d) - 1;
-    Fe x, y;
-    const Q4* q = reinterpret_cast<const Q4*>(gtab) + 4 * e;
+// ---- the fixed-base half u1*G from the positional table (ptab.h): `pos` mixed additions, no doublings ----
+// entry |d| of window j: affine x || y in the internal form (d == 0 loads entry 1; the caller discards it)
+SG_HD void sw_ptab_load(Fe& x, Fe& y, const PTab& t, u32 j, int d) {
+    const Q4* q = reinterpret_cast<const Q4*>(t.base + ptab_offset(t, j, d, 16));
     Q4 a = q[0], b = q[1], c = q[2], dd = q[3];
     x.v[0] = a.x; x.v[1] = a.y; x.v[2] = a.z; x.v[3] = a.w;
     x.v[4] = b.x; x.v[5] = b.y; x.v[6] = b.z; x.v[7] = b.w;
     y.v[0] = c.x; y.v[1] = c.y; y.v[2] = c.z; y.v[3] = c.w;
     y.v[4] = dd.x; y.v[5] = dd.y; y.v[6] = dd.z; y.v[7] = dd.w;
-    if ((d < 0) != flip) F::neg(y, y);
-    jac_madd<C>(acc, x, y);
 }
 
-// Entry j (1-based multiple) of a fixed-base table: j*G (or lambda*j*G) as affine x || y in the internal form.
-// g_xy: the generator in internal form (16 words).  Runs once per entry at init (device) or at load (host simulation).
+// acc = sum_j d_j * T[j]  =  2^-D * u1 * G  (infinity when u1 = 0).  The entry of the next window is loaded before the
+// current addition so that the gather (HBM / L2, a different line per lane) hides behind ~11 field products.
 template <class C>
-SG_HD void sw_gtab_entry(u32* out16, u32 j, bool endo, const u32* g_xy) {
+SG_HD void sw_ptab_sum(JacPoint& acc, const u32* u1, const PTab& t) {
+    typedef typename C::F F;
+    acc.inf = true;
+    F::set_zero(acc.X);
+    F::set_zero(acc.Y);
+    F::set_zero(acc.Z);
+    u32 kp[9];
+    ptab_recode(kp, u1, t);
+    int d = ptab_pop_digit(kp, t.w);
+    Fe x, y;
+    sw_ptab_load(x, y, t, 0, d);
+#pragma unroll 1
+    for (u32 j = 0; j < t.pos; j++) {
+        Fe xn = x, yn = y;
+        int dn = 0;
+        if (j + 1 < t.pos) {
+            dn = ptab_pop_digit(kp, t.w);
+            sw_ptab_load(xn, yn, t, j + 1, dn);
+        }
+        if (d != 0) {
+            if (d < 0) F::neg(y, y);
+            jac_madd<C>(acc, x, y);
+        }
+        x = xn;
+        y = yn;
+        d = dn;
+    }
+}
+
+// Table generation (once per device at init, or at load in the host simulation).
+// Window base B_j = 2^(w j) * pt0: `ndbl` = w j doublings of the seed, affine x || y in the internal form.
+template <class C>
+SG_HD void sw_ptab_base(u32* out16, u32 ndbl) {
+    typedef typename C::F F;
+    JacPoint P;
+    F::from_table(P.X, C::pt0());
+    F::from_table(P.Y, C::pt0() + 8);
+    F::set_one(P.Z);
+    P.inf = false;
+#pragma unroll 1
+    for (u32 i = 0; i < ndbl; i++) jac_dbl<C>(P);
+    Fe zi, zi2, ax, ay;
+    fe_inv((F*)0, zi, P.Z);
+    F::sqr(zi2, zi);
+    F::mul(ax, P.X, zi2);
+    F::mul(zi2, zi2, zi);
+    F::mul(ay, P.Y, zi2);
+    F::normalize(ax, ax);
+    F::normalize(ay, ay);
+    copy8(out16, ax.v);
+    copy8(out16 + 8, ay.v);
+}
+
+// Entry m * B (1 <= m <= 2^(w-1)) by double-and-add over the w bits of m
+template <class C>
+SG_HD void sw_ptab_entry(u32* out16, u32 m, u32 w, const u32* base16) {
     typedef typename C::F F;
     Fe gx, gy;
-    F::from_table(gx, g_xy);
-    F::from_table(gy, g_xy + 8);
+    F::from_table(gx, base16);
+    F::from_table(gy, base16 + 8);
     JacPoint P;
     P.inf = true;
     F::set_zero(P.X);
     F::set_zero(P.Y);
     F::set_zero(P.Z);
 #pragma unroll 1
-    for (int b = kGWin - 1; b >= 0; b--) {
+    for (int b = (int)w - 1; b >= 0; b--) {
         jac_dbl<C>(P);
-        if ((j >> b) & 1u) jac_madd<C>(P, gx, gy);
+        if ((m >> b) & 1u) jac_madd<C>(P, gx, gy);
     }
     Fe zi, zi2, ax, ay;
     fe_inv((F*)0, zi, P.Z);
@@ -418,16 +476,15 @@ SG_HD void sw_gtab_entry(u32* out16, u32 j, bool endo, const u32* g_xy) {
     F::mul(ax, P.X, zi2);
     F::mul(zi2, zi2, zi);
     F::mul(ay, P.Y, zi2);
-    if (C::kGlv && endo) C::mul_beta(ax, ax);
     F::normalize(ax, ax);
     F::normalize(ay, ay);
     copy8(out16, ax.v);
     copy8(out16 + 8, ay.v);
 }
 
-// Q = u1*G + u2*R.  secp256k1: u1, u2 are GLV-split into four <=128-bit streams; 33 signed 4-bit windows for the two
-// R streams and 11 signed 12-bit windows for the two G streams share 128 doublings.  secp256r1: two 256-bit streams,
-// 65 / 22 windows over 256 doublings.
+// Q = u1*G + u2*R.  The accumulator starts as 2^-D u1 G (sw_ptab_sum); then secp256k1 runs the two GLV halves of u2
+// (<= 129 bits each) as 33 signed 4-bit windows sharing D = 128 doublings, secp256r1 one 256-bit stream of 65 windows over
+// D = 256 doublings.
 // Block-wide rendezvous between the phases of the per-signature program.  The fused kernels run one 512-thread block per
 // SM and keep its 16 warps in the same few KB of code at any time: the whole program is ~170 KB of SASS against a
 // 32 KB L1.5 / 6 KB L0 instruction cache, and letting warps drift apart cost 12-27% (profiles/r01_variants.md).
@@ -448,40 +505,28 @@ SG_HD void phase_sync() {
 #define SG_PRAGMA_UNROLL(n) SG_PRAGMA_(unroll n)
 
 template <class C, bool kSync>
-SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabRef& tab, const u32* gtab,
-                         const u32* gtab_global) {
-    // gtab: the j*G table (possibly the shared-memory copy); gtab_global: the full table in global memory, whose second
-    // half holds lambda*j*G for secp256k1
+SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabRef& tab, const PTab& gt) {
 #if defined(SG_HOT_DBL_ONLY)
     typedef typename C::Cold HA;  // additions with out-of-line products, doublings inlined
 #else
     typedef typename C::Hot HA;
 #endif
     typedef typename C::Hot H;
-    acc.inf = true;
-    C::F::set_zero(acc.X);
-    C::F::set_zero(acc.Y);
-    C::F::set_zero(acc.Z);
+    sw_ptab_sum<typename C::Cold>(acc, u1, gt);
     if (C::kGlv) {
-        GlvSplit sr, sg;
+        static_assert(!C::kGlv || kPTabShiftK1 == 32 * 4, "the table's scale follows the loop's doublings");
+        GlvSplit sr;
         k1_glv_split(sr, u2);
-        k1_glv_split(sg, u1);
-        u32 kp[4][6];
+        u32 kp[2][6];
 #pragma unroll
         for (int i = 0; i < 5; i++) {
             kp[0][i] = sr.k1[i];
             kp[1][i] = sr.k2[i];
-            kp[2][i] = sg.k1[i];
-            kp[3][i] = sg.k2[i];
         }
-#pragma unroll
-        for (int s = 0; s < 4; s++) kp[s][5] = 0;
+        kp[0][5] = kp[1][5] = 0;
         recode_offset<5, 4, 33>(kp[0]);
         recode_offset<5, 4, 33>(kp[1]);
-        recode_offset<5, kGWin, 11>(kp[2]);
-        recode_offset<5, kGWin, 11>(kp[3]);
-        const bool flip[4] = {sr.neg1, sr.neg2, sg.neg1, sg.neg2};
-        int gcount = 0;  // i % 3 without a division: G windows sit on every third R window
+        const bool flip[2] = {sr.neg1, sr.neg2};
 #pragma unroll 1
         for (int i = 32; i >= 0; i--) {
             phase_sync<kSync>();
@@ -496,31 +541,14 @@ SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabR
             }
 #pragma unroll 1
             for (int s = 0; s < 2; s++) sw_add_from_table<HA>(acc, tab, recode_digit<4>(kp[s], i), flip[s], s == 1);
-            // i = 30, 27, ..., 0  <->  G window i / 3 = 10 ... 0   (i = 32, 31 carry no G window)
-            if (i <= 30) {
-                if (gcount == 0) {
-#pragma unroll 1
-                    for (int s = 2; s < 4; s++)
-                        sw_add_from_gtab<HA>(acc, s == 3 ? gtab_global + kGTabEntries * 16 : gtab,
-                                            recode_digit<kGWin>(kp[s], (i * 11) >> 5 /* i / 3 for i <= 30 */), flip[s]);
-                    gcount = 2;
-                } else {
-                    gcount--;
-                }
-            }
         }
     } else {
-        u32 kp[2][10];
+        static_assert(C::kGlv || kPTabShiftR1 == 64 * 4, "the table's scale follows the loop's doublings");
+        u32 kp[10];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            kp[0][i] = u2[i];
-            kp[1][i] = u1[i];
-        }
-        kp[0][8] = kp[0][9] = 0;
-        kp[1][8] = kp[1][9] = 0;
-        recode_offset<9, 4, 65>(kp[0]);
-        recode_offset<9, kGWin, 22>(kp[1]);
-        int gcount = 0;
+        for (int i = 0; i < 8; i++) kp[i] = u2[i];
+        kp[8] = kp[9] = 0;
+        recode_offset<9, 4, 65>(kp);
 #pragma unroll 1
         for (int i = 64; i >= 0; i--) {
             phase_sync<kSync>();
@@ -533,16 +561,7 @@ SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabR
                     jac_dbl<H>(acc);
                 }
             }
-            sw_add_from_table<HA>(acc, tab, recode_digit<4>(kp[0], i), false, false);
-            // i = 63, 60, ..., 0  <->  G window i / 3 = 21 ... 0
-            if (i <= 63) {
-                if (gcount == 0) {
-                    sw_add_from_gtab<HA>(acc, gtab, recode_digit<kGWin>(kp[1], (i * 43) >> 7 /* i / 3 for i < 128 */), false);
-                    gcount = 2;
-                } else {
-                    gcount--;
-                }
-            }
+            sw_add_from_table<HA>(acc, tab, recode_digit<4>(kp, i), false, false);
         }
     }
 }
@@ -557,9 +576,13 @@ SG_HD void sw_double_mul(JacPoint& acc, const u32* u1, const u32* u2, const TabR
 // sig_w / msg_w are the 64 / 32 input bytes as little-endian-loaded 32-bit words; out_w is X || Y big-endian bytes (again
 // as LE-loaded words), all zero when the status is 1 = invalid signature (the CPU libraries' Err(InvalidSignature)).
 // Per-thread scratch, in 16-byte chunks: B tables of kSwTabChunks, then per signature the r-chain slot (2), the
-// Jacobian result (6) and the Z-chain slot (2).
+// Jacobian result (6) and the Z-chain slot (2).  kSwBatch = 16 (17.9 KB of scratch per thread, 1.4 GB per device): a
+// 1,048,576-signature launch is 14 passes = ONE batch; 8 measured 0.9% slower (profiles/r02_variants.md).
 // ---------------------------------------------------------------------------------------------------------
-static constexpr int kSwBatch = 8;
+#ifndef SG_BATCH
+#define SG_BATCH 16
+#endif
+static constexpr int kSwBatch = SG_BATCH;
 static constexpr int kSwBatchChunks = kSwBatch * (kSwTabChunks + 10);
 
 SG_HD TabRef tab_offset(const TabRef& t, int chunks) {
@@ -598,7 +621,7 @@ SG_HD void sw_parse(SwParsed& p, const u32* sig_w, const u32* msg_w) {
 }
 
 template <class C, bool kSync, class IO>
-SG_HD void sw_ecrecover_batch(int B, IO& io, const TabRef& scratch, const u32* gtab, const u32* gtab_global) {
+SG_HD void sw_ecrecover_batch(int B, IO& io, const TabRef& scratch, const PTab& gt) {
     typedef typename C::F F;
     typedef typename C::S S;
     const int kSA = kSwBatch * kSwTabChunks, kQ = kSA + 2 * kSwBatch, kZP = kQ + 6 * kSwBatch;
@@ -660,8 +683,8 @@ SG_HD void sw_ecrecover_batch(int B, IO& io, const TabRef& scratch, const u32* g
             F::sqr(y2, y);
             if (!F::eq(y2, t)) {  // x = r is not on the curve: invalid; continue with R = G
                 bad |= 1u << j;
-                F::from_table(x, gtab);
-                F::from_table(y, gtab + 8);
+                F::from_table(x, C::gen());
+                F::from_table(y, C::gen() + 8);
             }
             {
                 u32 yp[8];
@@ -696,7 +719,7 @@ SG_HD void sw_ecrecover_batch(int B, IO& io, const TabRef& scratch, const u32* g
             S::mmul(u1, rinv.v, p.z);
             S::neg(u1, u1);
             JacPoint Q;
-            sw_double_mul<C, kSync>(Q, u1, u2, tab_offset(scratch, j * kSwTabChunks), gtab, gtab_global);
+            sw_double_mul<C, kSync>(Q, u1, u2, tab_offset(scratch, j * kSwTabChunks), gt);
             if (Q.inf) {  // Q = infinity: invalid; keep the chain invertible
                 bad |= 1u << j;
                 F::set_one(Q.Z);

@@ -473,8 +473,8 @@ SG_HD void pj_madd_g(Fe& X, Fe& Y, Fe& Z, const Fe& x2, const Fe& y2, bool commi
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Q = u1*G + u2*R with the group operations above.  The window schedule is sw_double_mul's (curve_sw.cuh): secp256k1 four
-// GLV streams over 128 doublings, secp256r1 two streams over 256.  Table layout (per signature, shared memory): entry e
+// Q = u1*G + u2*R with the group operations above.  The schedule is sw_double_mul's (curve_sw.cuh): the positional-table
+// sum first, then secp256k1's two GLV streams of u2 over 128 doublings, secp256r1's one stream over 256.  Table layout (per signature, shared memory): entry e
 // ((e+1) R): x at 4e, y at 4e + 2 (sw_build_table), beta*x at kSwTabChunks + 4e, -y at kSwTabChunks + 4e + 2.
 // ---------------------------------------------------------------------------------------------------------
 template <class C>
@@ -486,46 +486,50 @@ SG_HD void sw_group_add_r(Fe& X, Fe& Y, Fe& Z, const TabRef& tab, int d, bool fl
     pj_madd_g<C>(X, Y, Z, x, y, d != 0, g);
 }
 
-// fixed-base entry |d| * G from the table in global memory (L2: ~700 cycles for a lone warp -- issued before the window's
-// doublings so that the latency is hidden behind them)
-SG_HD void sw_group_load_g(Fe& x, Fe& y, const u32* gtab, int d) {
-    const int e = d == 0 ? 0 : (d < 0 ? -d : d) - 1;
-    const Q4* q = reinterpret_cast<const Q4*>(gtab) + 4 * e;
-    Q4 a = q[0], b = q[1], c = q[2], dd = q[3];
-    x.v[0] = a.x; x.v[1] = a.y; x.v[2] = a.z; x.v[3] = a.w;
-    x.v[4] = b.x; x.v[5] = b.y; x.v[6] = b.z; x.v[7] = b.w;
-    y.v[0] = c.x; y.v[1] = c.y; y.v[2] = c.z; y.v[3] = c.w;
-    y.v[4] = dd.x; y.v[5] = dd.y; y.v[6] = dd.z; y.v[7] = dd.w;
-}
-
+// kp / flips: the recoded scalars (sw_group_recode).  secp256k1: the two GLV halves of u2 (2 x 6 words, 2 flip bits), then
+// u1 + the positional table's offset (9 words); secp256r1: u2 (10 words), then u1 + offset (9 words).
 template <class C>
-SG_HD void sw_group_add_g(Fe& X, Fe& Y, Fe& Z, const Fe& x, Fe y, int d, bool flip, const GroupCtx& g) {
-    typedef typename C::F F;
-    if ((d < 0) != flip) F::neg(y, y);
-    pj_madd_g<C>(X, Y, Z, x, y, d != 0, g);
-}
+struct GroupKp {
+    static constexpr int kG = C::kGlv ? 12 : 10;  // where the fixed-base scalar starts
+    static constexpr int kWords = kG + 9;
+};
 
-// kp / flips: the recoded scalars as sw_double_mul builds them (secp256k1: 4 x 6 words + 4 flip bits; secp256r1: 2 x 10)
+// The fixed-base half first: X:Y:Z = 2^-D u1 G as `pos` group additions of positional-table entries (ptab.h).  Every role
+// loads the entry (the same lines for all the warps of the block); the next one is requested before the current addition.
 template <class C>
-SG_HD void sw_double_mul_g(Fe& X, Fe& Y, Fe& Z, const u32* kp, u32 flips, const TabRef& tab, const u32* gtab_global,
-                           const GroupCtx& g) {
+SG_HD void sw_group_ptab_sum(Fe& X, Fe& Y, Fe& Z, const u32* gk9, const PTab& gt, const GroupCtx& g) {
     typedef typename C::F F;
     F::set_zero(X);
     F::set_one(Y);
     F::set_zero(Z);
+    u32 gk[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) gk[i] = gk9[i];
+    int d = ptab_pop_digit(gk, gt.w);
+    Fe x, y;
+    sw_ptab_load(x, y, gt, 0, d);
+#pragma unroll 1
+    for (u32 j = 0; j < gt.pos; j++) {
+        Fe xn = x, yn = y;
+        int dn = 0;
+        if (j + 1 < gt.pos) {
+            dn = ptab_pop_digit(gk, gt.w);
+            sw_ptab_load(xn, yn, gt, j + 1, dn);
+        }
+        if (d < 0) F::neg(y, y);
+        pj_madd_g<C>(X, Y, Z, x, y, d != 0, g);
+        x = xn;
+        y = yn;
+        d = dn;
+    }
+}
+
+template <class C>
+SG_HD void sw_double_mul_g(Fe& X, Fe& Y, Fe& Z, const u32* kp, u32 flips, const TabRef& tab, const PTab& gt, const GroupCtx& g) {
+    sw_group_ptab_sum<C>(X, Y, Z, kp + GroupKp<C>::kG, gt, g);
     if (C::kGlv) {
-        int gcount = 0;
 #pragma unroll 1
         for (int i = 32; i >= 0; i--) {
-            const bool gwin = i <= 30 && gcount == 0;
-            int d2 = 0, d3 = 0;
-            Fe gx2, gy2, gx3, gy3;
-            if (gwin) {
-                d2 = recode_digit<kGWin>(kp + 12, (i * 11) >> 5);
-                d3 = recode_digit<kGWin>(kp + 18, (i * 11) >> 5);
-                sw_group_load_g(gx2, gy2, gtab_global, d2);
-                sw_group_load_g(gx3, gy3, gtab_global + kGTabEntries * 16, d3);
-            }
             if (i != 32) {
 #pragma unroll 1
                 for (int d = 0; d < 4; d++) pj_dbl_g<C>(X, Y, Z, g);
@@ -533,75 +537,42 @@ SG_HD void sw_double_mul_g(Fe& X, Fe& Y, Fe& Z, const u32* kp, u32 flips, const 
 #pragma unroll 1
             for (int s = 0; s < 2; s++)
                 sw_group_add_r<C>(X, Y, Z, tab, recode_digit<4>(kp + 6 * s, i), ((flips >> s) & 1u) != 0, s == 1, g);
-            if (i <= 30) {
-                if (gwin) {
-                    sw_group_add_g<C>(X, Y, Z, gx2, gy2, d2, ((flips >> 2) & 1u) != 0, g);
-                    sw_group_add_g<C>(X, Y, Z, gx3, gy3, d3, ((flips >> 3) & 1u) != 0, g);
-                    gcount = 2;
-                } else {
-                    gcount--;
-                }
-            }
         }
     } else {
-        int gcount = 0;
 #pragma unroll 1
         for (int i = 64; i >= 0; i--) {
-            const bool gwin = i <= 63 && gcount == 0;
-            int dg = 0;
-            Fe gx, gy;
-            if (gwin) {
-                dg = recode_digit<kGWin>(kp + 10, (i * 43) >> 7);
-                sw_group_load_g(gx, gy, gtab_global, dg);
-            }
             if (i != 64) {
 #pragma unroll 1
                 for (int d = 0; d < 4; d++) pj_dbl_g<C>(X, Y, Z, g);
             }
             sw_group_add_r<C>(X, Y, Z, tab, recode_digit<4>(kp, i), false, false, g);
-            if (i <= 63) {
-                if (gwin) {
-                    sw_group_add_g<C>(X, Y, Z, gx, gy, dg, false, g);
-                    gcount = 2;
-                } else {
-                    gcount--;
-                }
-            }
         }
     }
 }
 
-// recoded scalars for sw_double_mul_g: words of kp (24 for secp256k1, 20 for secp256r1) and the flip bits
+// recoded scalars for sw_double_mul_g (GroupKp<C>::kWords words) and the flip bits
 template <class C>
-SG_HD u32 sw_group_recode(u32* kp, const u32* u1, const u32* u2) {
+SG_HD u32 sw_group_recode(u32* kp, const u32* u1, const u32* u2, const PTab& gt) {
     u32 flips = 0;
     if (C::kGlv) {
-        GlvSplit sr, sg;
+        GlvSplit sr;
         k1_glv_split(sr, u2);
-        k1_glv_split(sg, u1);
 #pragma unroll
         for (int i = 0; i < 5; i++) {
             kp[i] = sr.k1[i];
             kp[6 + i] = sr.k2[i];
-            kp[12 + i] = sg.k1[i];
-            kp[18 + i] = sg.k2[i];
         }
-        kp[5] = kp[11] = kp[17] = kp[23] = 0;
+        kp[5] = kp[11] = 0;
         recode_offset<5, 4, 33>(kp);
         recode_offset<5, 4, 33>(kp + 6);
-        recode_offset<5, kGWin, 11>(kp + 12);
-        recode_offset<5, kGWin, 11>(kp + 18);
-        flips = (sr.neg1 ? 1u : 0u) | (sr.neg2 ? 2u : 0u) | (sg.neg1 ? 4u : 0u) | (sg.neg2 ? 8u : 0u);
+        flips = (sr.neg1 ? 1u : 0u) | (sr.neg2 ? 2u : 0u);
     } else {
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            kp[i] = u2[i];
-            kp[10 + i] = u1[i];
-        }
-        kp[8] = kp[9] = kp[18] = kp[19] = 0;
+        for (int i = 0; i < 8; i++) kp[i] = u2[i];
+        kp[8] = kp[9] = 0;
         recode_offset<9, 4, 65>(kp);
-        recode_offset<9, kGWin, 22>(kp + 10);
     }
+    ptab_recode(kp + GroupKp<C>::kG, u1, gt);
     return flips;
 }
 
@@ -625,13 +596,13 @@ SG_HD void sw_group_table(const TabRef& tab, const Fe& x, const Fe& y) {
 // One signature, kGroupRolesSw cooperating threads.  sig_w / msg_w: the input row (every role loads it); out_w / st are
 // written by role 0 (returns true there).  tab: the signature's work table (kGroupSwTabChunks chunks, shared by the roles).
 template <class C>
-SG_HD bool sw_ecrecover_group(const u32* sig_w, const u32* msg_w, u32* out_w, u32* st, const TabRef& tab, const u32* gtab,
+SG_HD bool sw_ecrecover_group(const u32* sig_w, const u32* msg_w, u32* out_w, u32* st, const TabRef& tab, const PTab& gtab,
                               const GroupCtx& g) {
     typedef typename C::F F;
     typedef typename C::S S;
     SwParsed p;
     sw_parse<C>(p, sig_w, msg_w);
-    constexpr int kKpWords = C::kGlv ? 24 : 20;
+    constexpr int kKpWords = GroupKp<C>::kWords;
     if (C::kAIsZero) {
         // secp256k1: the table of multiples of R is built WITHOUT y, in the shadow of the square-root chain.  With
         // w = x^3 + 7 = y^2, the map (X, Y) -> (X / w, y Y / w^2) sends E'' : Y^2 = X^3 + 7 w^3 onto the curve, and
@@ -688,8 +659,8 @@ SG_HD bool sw_ecrecover_group(const u32* sig_w, const u32* msg_w, u32* out_w, u3
         F::sqr(y2, y);
         if (!F::eq(y2, t)) {  // x = r is not on the curve: invalid; continue with R = G
             bad = 1u;
-            F::from_table(x, gtab);
-            F::from_table(y, gtab + 8);
+            F::from_table(x, C::gen());
+            F::from_table(y, C::gen() + 8);
         }
         {
             u32 yp[8];
@@ -707,7 +678,8 @@ SG_HD bool sw_ecrecover_group(const u32* sig_w, const u32* msg_w, u32* out_w, u3
         S::mmul(u2, rim, p.s);
         S::mmul(u1, rim, p.z);
         S::neg(u1, u1);
-        const u32 flips = sw_group_recode<C>(kp, u1, u2);
+        ptab_prefetch(gtab, u1, 16);  // the fixed-base entries travel to L2 while the other roles finish y and the table
+        const u32 flips = sw_group_recode<C>(kp, u1, u2, gtab);
 #pragma unroll
         for (int i = 0; i < kKpWords; i++) g.put_word(i, kp[i]);
         g.put_word(kKpWords, flips);
@@ -941,7 +913,7 @@ SG_HD void ed_tab_store_g(const TabRef& tab, int e, const EdPoint& P, const Grou
 
 // One signature, kGroupRolesEd cooperating threads; the verdict is returned by role 0 (the other roles return 0).
 // Role 0 decompresses A while role 1 hashes and reduces mod L; the table, the double-scalar loop and nothing else are shared.
-SG_HD u32 ed_verify_group(const u32* sig_w, const u32* msg_w, const u32* pk_w, const TabRef& tab, const u32* btab, const GroupCtx& g) {
+SG_HD u32 ed_verify_group(const u32* sig_w, const u32* msg_w, const u32* pk_w, const TabRef& tab, const PTab& btab, const GroupCtx& g) {
     typedef Sc<ModEdL> S;
 #if !defined(SG_NO_HOT_INLINE)
     typedef Inl<Fp25519> FH;
@@ -957,6 +929,7 @@ SG_HD u32 ed_verify_group(const u32* sig_w, const u32* msg_w, const u32* pk_w, c
         g.put(13, y);
         g.put_word(20, ok ? 1u : 0u);
     } else if (g.role == 1) {
+        ptab_prefetch(btab, sig_w + 8, 24);  // the fixed-base entries travel to L2 during the hash and the decompression
         u32 pre[24], dig[16], k[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -972,19 +945,11 @@ SG_HD u32 ed_verify_group(const u32* sig_w, const u32* msg_w, const u32* pk_w, c
         recode_offset<8, 4, 64>(kp);
 #pragma unroll
         for (int i = 0; i < 10; i++) g.put_word(i, kp[i]);
-        copy8(kp, sig_w + 8);
-        kp[8] = kp[9] = 0;
-        recode_offset<9, kGWin, 22>(kp);
-#pragma unroll
-        for (int i = 0; i < 10; i++) g.put_word(10 + i, kp[i]);
     }
     g.sync();
-    u32 kp[2][10];
+    u32 kp[10];
 #pragma unroll
-    for (int i = 0; i < 10; i++) {
-        kp[0][i] = g.get_word(i);
-        kp[1][i] = g.get_word(10 + i);
-    }
+    for (int i = 0; i < 10; i++) kp[i] = g.get_word(i);
     bool ok = g.get_word(20) != 0;
     // table {1..8} (-A): P1, 2P1, 3P1 = 2P1 + P1, 4P1 = 2 (2P1), 5P1 = 4P1 + P1, 6P1 = 2 (3P1), 7P1 = 6P1 + P1, 8P1 = 2 (4P1)
     {
@@ -1024,27 +989,38 @@ SG_HD u32 ed_verify_group(const u32* sig_w, const u32* msg_w, const u32* pk_w, c
         ed_tab_store_g<FH>(tab, 7, T, g);
     }
     g.sync();  // the table is complete before anyone reads it
+    // the fixed-base half first: acc = 2^-252 [s]B from the positional table (ptab.h), every role loading the entries
     EdPoint acc;
     ed_set_identity(acc);
-    int gcount = 0;
+    {
+        u32 sk[9];
+        ptab_recode(sk, sig_w + 8, btab);
+        int db = ptab_pop_digit(sk, btab.w);
+        Fe bypx, bymx, bxy2d;
+        ed_ptab_load(bypx, bymx, bxy2d, btab, 0, db);
+#pragma unroll 1
+        for (u32 j = 0; j < btab.pos; j++) {
+            Fe a = bypx, b = bymx, c = bxy2d;
+            int dn = 0;
+            if (j + 1 < btab.pos) {
+                dn = ptab_pop_digit(sk, btab.w);
+                ed_ptab_load(a, b, c, btab, j + 1, dn);
+            }
+            ed_add_g<FH>(acc, bypx, bymx, bypx, bxy2d, false, db < 0, db != 0, g);
+            bypx = a;
+            bymx = b;
+            bxy2d = c;
+            db = dn;
+        }
+    }
 #pragma unroll 1
     for (int i = 63; i >= 0; i--) {
-        const bool bwin = gcount == 0;
-        int db = 0;
-        Fe bypx, bymx, bxy2d;
-        if (bwin) {  // the fixed-base entry comes from L2: issue the loads before the window's doublings
-            db = recode_digit<kGWin>(kp[1], (i * 43) >> 7);
-            const int e = db == 0 ? 0 : (db < 0 ? -db : db) - 1;
-            ed_load_fe_words(bypx, btab + 24 * e);
-            ed_load_fe_words(bymx, btab + 24 * e + 8);
-            ed_load_fe_words(bxy2d, btab + 24 * e + 16);
-        }
         if (i != 63) {
 #pragma unroll 1
             for (int d = 0; d < 4; d++) ed_dbl_g<FH>(acc, g);
         }
         {
-            const int d = recode_digit<4>(kp[0], i);
+            const int d = recode_digit<4>(kp, i);
             const int e = d == 0 ? 0 : (d < 0 ? -d : d) - 1;
             Fe ypx, ymx, z2, t2d;
             tab_load_fe(ypx, tab, 8 * e + 0);
@@ -1052,12 +1028,6 @@ SG_HD u32 ed_verify_group(const u32* sig_w, const u32* msg_w, const u32* pk_w, c
             tab_load_fe(z2, tab, 8 * e + 4);
             tab_load_fe(t2d, tab, 8 * e + 6);
             ed_add_g<FH>(acc, ypx, ymx, z2, t2d, true, d < 0, d != 0, g);
-        }
-        if (bwin) {
-            ed_add_g<FH>(acc, bypx, bymx, bypx, bxy2d, false, db < 0, db != 0, g);
-            gcount = 2;
-        } else {
-            gcount--;
         }
     }
     if (g.role != 0) return 0u;
@@ -1072,10 +1042,10 @@ SG_HD u32 ed_verify_group(const u32* sig_w, const u32* msg_w, const u32* pk_w, c
 
 // ---- unit shims (the lane-group twins of K1/R1_DOUBLE_MUL and ED_MULPT): every role calls them; role 0 returns true ----
 template <class C>
-SG_HD bool unit_double_mul_g(u32* out, const u32* u1, const u32* u2, const u32* xy, const TabRef& tab, const u32* gtab,
+SG_HD bool unit_double_mul_g(u32* out, const u32* u1, const u32* u2, const u32* xy, const TabRef& tab, const PTab& gtab,
                              const GroupCtx& g) {
     typedef typename C::F F;
-    constexpr int kKpWords = C::kGlv ? 24 : 20;
+    constexpr int kKpWords = GroupKp<C>::kWords;
     if (g.role == 0) {
         Fe x, y;
         F::from_plain(x, xy);
@@ -1083,7 +1053,7 @@ SG_HD bool unit_double_mul_g(u32* out, const u32* u1, const u32* u2, const u32* 
         sw_group_table<C>(tab, x, y);
     } else if (g.role == 1) {
         u32 kp[kKpWords];
-        const u32 flips = sw_group_recode<C>(kp, u1, u2);
+        const u32 flips = sw_group_recode<C>(kp, u1, u2, gtab);
 #pragma unroll
         for (int i = 0; i < kKpWords; i++) g.put_word(i, kp[i]);
         g.put_word(kKpWords, flips);

@@ -12,8 +12,7 @@ namespace sigops {
 __global__ void __launch_bounds__(kBlock, SG_MINB_ED) ed25519_verify_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
                                                                             const Q4* __restrict__ pks, size_t n,
                                                                             uint8_t* __restrict__ valid, Q4* __restrict__ scratch,
-                                                                            const u32* __restrict__ btab_g, u32 smem_words) {
-    const u32* btab = stage_table(btab_g, smem_words);
+                                                                            const __grid_constant__ PTab btab) {
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     TabRef tab;
@@ -35,7 +34,7 @@ __global__ void __launch_bounds__(kBlock, SG_MINB_ED) ed25519_verify_kernel(cons
 __global__ void __launch_bounds__(kBlock, SG_MINB_ED) ed25519_verify_msgs_kernel(
     const Q4* __restrict__ sigs, const uint8_t* __restrict__ msg_bytes, const unsigned long long* __restrict__ msg_off,
     const Q4* __restrict__ pks, size_t n, int strict, uint8_t* __restrict__ valid, Q4* __restrict__ scratch,
-    const u32* __restrict__ btab) {
+    const __grid_constant__ PTab btab) {
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     TabRef tab;
@@ -70,21 +69,18 @@ __global__ void __launch_bounds__(kBlock, SG_MINB_ED) ed25519_verify_msgs_kernel
 }
 
 int kl_ed_verify(const KLaunch& l, const void* sigs, const void* msgs, const void* pks, size_t n, uint8_t* valid, void* scratch,
-                 const u32* btab, u32 smem_words) {
-    ed25519_verify_kernel<<<l.grid, l.tpb, (size_t)smem_words * 4, l.stream>>>((const Q4*)sigs, (const Q4*)msgs, (const Q4*)pks, n, valid,
-                                                                              (Q4*)scratch, btab, smem_words);
+                 const PTab& btab) {
+    ed25519_verify_kernel<<<l.grid, l.tpb, 0, l.stream>>>((const Q4*)sigs, (const Q4*)msgs, (const Q4*)pks, n, valid, (Q4*)scratch, btab);
     return (int)cudaGetLastError();
 }
 int kl_ed_verify_msgs(const KLaunch& l, const void* sigs, const uint8_t* msg_bytes, const unsigned long long* msg_off, const void* pks,
-                      size_t n, int strict, uint8_t* valid, void* scratch, const u32* btab) {
+                      size_t n, int strict, uint8_t* valid, void* scratch, const PTab& btab) {
     ed25519_verify_msgs_kernel<<<l.grid, l.tpb, 0, l.stream>>>((const Q4*)sigs, msg_bytes, msg_off, (const Q4*)pks, n, strict, valid,
                                                               (Q4*)scratch, btab);
     return (int)cudaGetLastError();
 }
 int kl_ed_setup(int* max_blocks_per_sm, int* max_blocks_per_sm_msgs) {
-    cudaError_t e = cudaFuncSetAttribute(ed25519_verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGTabEntries * 24 * 4);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, ed25519_verify_kernel, kBlock, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, ed25519_verify_kernel, kBlock, 0);
     if (e != cudaSuccess) return (int)e;
     return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm_msgs, ed25519_verify_msgs_kernel, kBlock, 0);
 }

@@ -12,7 +12,7 @@ namespace sigops {
 __global__ void __launch_bounds__(kGroupRolesEd * 32) ed25519_verify_group_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
                                                                                   const Q4* __restrict__ pks, size_t n,
                                                                                   uint8_t* __restrict__ valid,
-                                                                                  const u32* __restrict__ btab) {
+                                                                                  const __grid_constant__ PTab btab) {
     extern __shared__ __align__(16) u32 sg_group_smem[];
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
     Q4* mb = reinterpret_cast<Q4*>(sg_group_smem);
@@ -59,7 +59,8 @@ __global__ void __launch_bounds__(kGroupRolesEd * 32) ed25519_verify_group_kerne
 
 // unit shim: one item per lane, the roles of a block cooperate on 32 items (ops SIGOPS_UNIT_*_GROUP_*)
 __global__ void __launch_bounds__(kGroupRolesSw * 32) unit_group_kernel(int op, const u32* __restrict__ in, size_t n, u32* __restrict__ out,
-                                                                        const u32* k1g, const u32* r1g) {
+                                                                        const __grid_constant__ PTab k1g,
+                                                                        const __grid_constant__ PTab r1g) {
     extern __shared__ __align__(16) u32 sg_group_smem[];
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
     Q4* mb = reinterpret_cast<Q4*>(sg_group_smem);
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(kGroupRolesSw * 32) unit_group_kernel(int op, 
     }
 }
 
-int kl_ed_group(const KLaunch& l, const void* sigs, const void* msgs, const void* pks, size_t n, uint8_t* valid, const u32* btab) {
+int kl_ed_group(const KLaunch& l, const void* sigs, const void* msgs, const void* pks, size_t n, uint8_t* valid, const PTab& btab) {
     ed25519_verify_group_kernel<<<l.grid, kGroupRolesEd * 32, kGroupEdSmem, l.stream>>>((const Q4*)sigs, (const Q4*)msgs, (const Q4*)pks, n,
                                                                                        valid, btab);
     return (int)cudaGetLastError();
@@ -106,7 +107,7 @@ int kl_ed_group_setup(int* max_blocks_per_sm) {
     return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, ed25519_verify_group_kernel, kGroupRolesEd * 32,
                                                               kGroupEdSmem);
 }
-int kl_unit_group(const KLaunch& l, int op, const u32* in, size_t n, u32* out, const u32* k1g, const u32* r1g) {
+int kl_unit_group(const KLaunch& l, int op, const u32* in, size_t n, u32* out, const PTab& k1g, const PTab& r1g) {
     const int roles = op == SIGOPS_UNIT_ED_GROUP_MULPT ? kGroupRolesEd : kGroupRolesSw;
     unit_group_kernel<<<l.grid, roles * 32, kGroupSwSmem, l.stream>>>(op, in, n, out, k1g, r1g);
     return (int)cudaGetLastError();

@@ -14,7 +14,7 @@ template <class C>
 __global__ void __launch_bounds__(kGroupRolesSw * 32) ecrecover_group_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
                                                                              size_t n, Q4* __restrict__ out,
                                                                              uint8_t* __restrict__ status,
-                                                                             const u32* __restrict__ gtab) {
+                                                                             const __grid_constant__ PTab gtab) {
     extern __shared__ __align__(16) u32 sg_group_smem[];
     const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
     Q4* mb = reinterpret_cast<Q4*>(sg_group_smem);
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kGroupRolesSw * 32) ecrecover_group_kernel(con
 
 template <class C>
 int launch_ecrecover_group(const KLaunch& l, const void* sigs, const void* msgs, size_t n, void* out, uint8_t* status,
-                           const u32* gtab) {
+                           const PTab& gtab) {
     ecrecover_group_kernel<C><<<l.grid, kGroupRolesSw * 32, kGroupSwSmem, l.stream>>>((const Q4*)sigs, (const Q4*)msgs, n, (Q4*)out,
                                                                                      status, gtab);
     return (int)cudaGetLastError();

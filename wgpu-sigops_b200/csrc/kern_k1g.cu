@@ -2,7 +2,7 @@
 #include "kern_group_sw.cuh"
 
 namespace sigops {
-int kl_k1_group(const KLaunch& l, const void* sigs, const void* msgs, size_t n, void* out, uint8_t* status, const u32* gtab) {
+int kl_k1_group(const KLaunch& l, const void* sigs, const void* msgs, size_t n, void* out, uint8_t* status, const PTab& gtab) {
     return launch_ecrecover_group<CurveK1>(l, sigs, msgs, n, out, status, gtab);
 }
 int kl_k1_group_setup(int* max_blocks_per_sm) { return setup_ecrecover_group<CurveK1>(max_blocks_per_sm); }

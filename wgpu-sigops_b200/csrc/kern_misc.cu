@@ -35,28 +35,43 @@ __global__ void __launch_bounds__(256) sha256_pubkeys_kernel(const u32* __restri
     for (int j = 0; j < 8; j++) out[i * 8 + j] = bad ? 0u : d[j];
 }
 
-// Fixed-base tables, generated once per device at init: thread j writes entry j (the (j+1)-th multiple) of
-//   k1tab  [2][kGTabEntries][16]  j*G and lambda*j*G        r1tab [kGTabEntries][16]  j*G (Montgomery form)
-//   edtab  [kGTabEntries][24]     j*B as affine Niels triples
-// from the baked single generators (consts_gen.cuh).  Replaces the 16-entry tables of src/precompute.rs:14-69 that the
-// reference uploads on every call (src/secp256k1_ecdsa.rs:108).
-__global__ void __launch_bounds__(64) gen_tables_kernel(u32* k1tab, u32* r1tab, u32* edtab) {
+// Positional fixed-base tables (ptab.h), generated once per device at init from the baked seeds 2^-D G (consts_gen.cuh).
+// Replaces the 16-entry tables of src/precompute.rs:14-69 that the reference uploads on every call
+// (src/secp256k1_ecdsa.rs:108).  Two launches per curve: the window bases B_j = 2^(w j) * seed (one thread each), then one
+// thread per entry m * B_j (w doublings, ~w/2 additions and one inversion: about a fifth of a signature).
+template <int CURVE>
+__global__ void __launch_bounds__(64) gen_ptab_bases_kernel(u32* bases, u32 w, u32 pos) {
     const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= (u32)kGTabEntries) return;
+    if (j >= pos) return;
     u32 e[24];
-    sw_gtab_entry<CurveK1>(e, j + 1, false, k1_g_dev);
-    for (int i = 0; i < 16; i++) k1tab[(size_t)j * 16 + i] = e[i];
-    sw_gtab_entry<CurveK1>(e, j + 1, true, k1_g_dev);
-    for (int i = 0; i < 16; i++) k1tab[((size_t)kGTabEntries + j) * 16 + i] = e[i];
-    sw_gtab_entry<CurveR1>(e, j + 1, false, r1_g_dev);
-    for (int i = 0; i < 16; i++) r1tab[(size_t)j * 16 + i] = e[i];
-    ed_btab_entry(e, j + 1, ed_b_niels_dev);
-    for (int i = 0; i < 24; i++) edtab[(size_t)j * 24 + i] = e[i];
+    if (CURVE == 0) sw_ptab_base<CurveK1>(e, w * j);
+    if (CURVE == 1) sw_ptab_base<CurveR1>(e, w * j);
+    if (CURVE == 2) ed_ptab_base(e, w * j);
+    const int words = CURVE == 2 ? 24 : 16;
+    for (int i = 0; i < words; i++) bases[(size_t)j * words + i] = e[i];
+}
+
+template <int CURVE>
+__global__ void __launch_bounds__(128) gen_ptab_kernel(u32* tab, const u32* __restrict__ bases, u32 w, u32 pos) {
+    const size_t per = (size_t)1 << (w - 1);
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= per * pos) return;
+    const u32 j = (u32)(t >> (w - 1)), m = (u32)(t & (per - 1)) + 1u;
+    const int words = CURVE == 2 ? 24 : 16;
+    u32 e[24];
+    if (CURVE == 0) sw_ptab_entry<CurveK1>(e, m, w, bases + (size_t)j * words);
+    if (CURVE == 1) sw_ptab_entry<CurveR1>(e, m, w, bases + (size_t)j * words);
+    if (CURVE == 2) ed_ptab_entry(e, m, w, bases + (size_t)j * words);
+    Q4* dst = reinterpret_cast<Q4*>(tab + t * words);
+    for (int q = 0; q < words / 4; q++) {
+        Q4 v = {e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]};
+        dst[q] = v;
+    }
 }
 
 __global__ void __launch_bounds__(kBlock) unit_kernel(int op, const u32* __restrict__ in, size_t n, u32* __restrict__ out,
-                                                      Q4* __restrict__ scratch, const u32* k1g, const u32* r1g,
-                                                      const u32* edb) {
+                                                      Q4* __restrict__ scratch, const __grid_constant__ PTab k1g,
+                                                      const __grid_constant__ PTab r1g, const __grid_constant__ PTab edb) {
     int in_w, out_w;
     unit_shape(op, in_w, out_w);
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
@@ -169,11 +184,29 @@ int kl_sha256_pubkeys(cudaStream_t st, const u32* pubkeys, const uint8_t* status
     sha256_pubkeys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pubkeys, status, n, out);
     return (int)cudaGetLastError();
 }
-int kl_gen_tables(cudaStream_t st, u32* k1tab, u32* r1tab, u32* edtab) {
-    gen_tables_kernel<<<(kGTabEntries + 63) / 64, 64, 0, st>>>(k1tab, r1tab, edtab);
+int kl_gen_ptab(cudaStream_t st, int curve, u32 w, u32* bases, u32* tab) {
+    const u32 pos = ptab_positions(w);
+    const size_t entries = ptab_entries(w);
+    const unsigned gb = (pos + 63) / 64, ge = (unsigned)((entries + 127) / 128);
+    switch (curve) {
+        case 0:
+            gen_ptab_bases_kernel<0><<<gb, 64, 0, st>>>(bases, w, pos);
+            gen_ptab_kernel<0><<<ge, 128, 0, st>>>(tab, bases, w, pos);
+            break;
+        case 1:
+            gen_ptab_bases_kernel<1><<<gb, 64, 0, st>>>(bases, w, pos);
+            gen_ptab_kernel<1><<<ge, 128, 0, st>>>(tab, bases, w, pos);
+            break;
+        case 2:
+            gen_ptab_bases_kernel<2><<<gb, 64, 0, st>>>(bases, w, pos);
+            gen_ptab_kernel<2><<<ge, 128, 0, st>>>(tab, bases, w, pos);
+            break;
+        default:
+            return -1;
+    }
     return (int)cudaGetLastError();
 }
-int kl_unit(const KLaunch& l, int op, const u32* in, size_t n, u32* out, void* scratch, const u32* k1g, const u32* r1g, const u32* edb) {
+int kl_unit(const KLaunch& l, int op, const u32* in, size_t n, u32* out, void* scratch, const PTab& k1g, const PTab& r1g, const PTab& edb) {
     unit_kernel<<<l.grid, l.tpb, 0, l.stream>>>(op, in, n, out, (Q4*)scratch, k1g, r1g, edb);
     return (int)cudaGetLastError();
 }

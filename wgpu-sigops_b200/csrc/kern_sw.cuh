@@ -13,10 +13,7 @@ namespace sigops {
 template <class C>
 __global__ void __launch_bounds__(kBlock, SG_MINB_SW) ecrecover_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
                                                                        size_t n, Q4* __restrict__ out, uint8_t* __restrict__ status,
-                                                                       Q4* __restrict__ scratch, const u32* __restrict__ gtab_g,
-                                                                       u32 smem_words) {
-    // secp256k1: the j*G half of the table is staged (the lambda*j*G half stays in L2); secp256r1: the whole table
-    const u32* gtab_s = stage_table(gtab_g, smem_words);
+                                                                       Q4* __restrict__ scratch, const __grid_constant__ PTab gtab) {
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     TabRef tab;
@@ -30,22 +27,19 @@ __global__ void __launch_bounds__(kBlock, SG_MINB_SW) ecrecover_kernel(const Q4*
         const int B = (int)((passes - pass) < (size_t)kSwBatch ? (passes - pass) : (size_t)kSwBatch);
         phase_sync<true>();
         io.first = pass * nthreads + gid;
-        sw_ecrecover_batch<C, kInnerSync>(B, io, tab, gtab_s, gtab_g);
+        sw_ecrecover_batch<C, kInnerSync>(B, io, tab, gtab);
     }
 }
 
 template <class C>
 int launch_ecrecover(const KLaunch& l, const void* sigs, const void* msgs, size_t n, void* out, uint8_t* status, void* scratch,
-                     const u32* gtab, u32 smem_words) {
-    ecrecover_kernel<C><<<l.grid, l.tpb, (size_t)smem_words * 4, l.stream>>>((const Q4*)sigs, (const Q4*)msgs, n, (Q4*)out, status,
-                                                                            (Q4*)scratch, gtab, smem_words);
+                     const PTab& gtab) {
+    ecrecover_kernel<C><<<l.grid, l.tpb, 0, l.stream>>>((const Q4*)sigs, (const Q4*)msgs, n, (Q4*)out, status, (Q4*)scratch, gtab);
     return (int)cudaGetLastError();
 }
 
 template <class C>
 int setup_ecrecover(int* max_blocks_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(ecrecover_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGTabEntries * 16 * 4);
-    if (e != cudaSuccess) return (int)e;
     return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, ecrecover_kernel<C>, kBlock, 0);
 }
 

@@ -40,19 +40,6 @@ static constexpr bool kInnerSync = true;
 
 #if defined(__CUDACC__)
 
-// Fixed-base table staged in shared memory: with one block per SM the whole 227 KB is free, and a 2048-entry table
-// (128 KB for the secp curves' j*G, 192 KB for ed25519's Niels triples) fits.  `smem_words` == 0 (small batches, where
-// the copy would cost more than the gathers) leaves the table in global memory / L2.
-extern __shared__ __align__(16) u32 sg_smem_table[];
-__device__ __forceinline__ const u32* stage_table(const u32* __restrict__ gtab, u32 smem_words) {
-    if (smem_words == 0) return gtab;
-    const Q4* src = reinterpret_cast<const Q4*>(gtab);
-    Q4* dst = reinterpret_cast<Q4*>(sg_smem_table);
-    for (u32 i = threadIdx.x; i < smem_words / 4; i += blockDim.x) dst[i] = src[i];
-    __syncthreads();
-    return sg_smem_table;
-}
-
 // Row access of one thread's batch: item j of the batch is row first + j * stride of the shard.  Rows past the end are
 // clamped on load (the thread redoes the last signature so that it reaches every barrier) and dropped on store.
 struct SwDeviceIO {
@@ -184,6 +171,9 @@ SG_HD void unit_shape(int op, int& in_w, int& out_w) {
             in_w = 24;
             out_w = 16;
             break;
+        case SIGOPS_UNIT_ED_FIXED_MUL:
+            out_w = 16;
+            break;
         case SIGOPS_UNIT_RAW_ADDSUB:
             in_w = 17;
             out_w = 16;
@@ -240,14 +230,14 @@ SG_HD void unit_field(int which, u32* out, const u32* in) {
 }
 
 template <class C>
-SG_HD void unit_double_mul(u32* out, const u32* u1, const u32* u2, const u32* xy, const TabRef& tab, const u32* gtab) {
+SG_HD void unit_double_mul(u32* out, const u32* u1, const u32* u2, const u32* xy, const TabRef& tab, const PTab& gtab) {
     typedef typename C::F F;
     Fe x, y;
     F::from_plain(x, xy);
     F::from_plain(y, xy + 8);
     sw_build_table<C>(tab, x, y);
     JacPoint Q;
-    sw_double_mul<C, false>(Q, u1, u2, tab, gtab, gtab);
+    sw_double_mul<C, false>(Q, u1, u2, tab, gtab);
     for (int i = 0; i < 17; i++) out[i] = 0;
     if (Q.inf) {
         out[16] = 1;
@@ -264,8 +254,8 @@ SG_HD void unit_double_mul(u32* out, const u32* u1, const u32* u2, const u32* xy
 }
 
 // dispatcher shared by the device shim kernel and the host simulation
-SG_HD void unit_dispatch(int op, u32* out, const u32* in, const TabRef& tab, const u32* k1g, const u32* r1g,
-                         const u32* edb) {
+SG_HD void unit_dispatch(int op, u32* out, const u32* in, const TabRef& tab, const PTab& k1g, const PTab& r1g,
+                         const PTab& edb) {
     switch (op) {
         case SIGOPS_UNIT_K1_MUL: case SIGOPS_UNIT_K1_SQR: case SIGOPS_UNIT_K1_ADD: case SIGOPS_UNIT_K1_SUB:
             unit_field<FpK1>(op - SIGOPS_UNIT_K1_MUL, out, in);
@@ -439,7 +429,19 @@ SG_HD void unit_dispatch(int op, u32* out, const u32* in, const TabRef& tab, con
             FE::mul(ay, acc.Y, zi);
             FE::to_plain(out, ax);
             FE::to_plain(out + 8, ay);
-            (void)edb;
+            break;
+        }
+        case SIGOPS_UNIT_ED_FIXED_MUL: {
+            // s * B through the positional table alone: the table's sum is 2^-252 s B, 252 doublings undo the scale
+            EdPoint acc;
+            ed_ptab_sum<FE>(acc, in, edb);
+            for (int i = 0; i < kPTabShiftEd; i++) ed_dbl<FE>(acc, false);
+            Fe zi, ax, ay;
+            fe_inv((FE*)0, zi, acc.Z);
+            FE::mul(ax, acc.X, zi);
+            FE::mul(ay, acc.Y, zi);
+            FE::to_plain(out, ax);
+            FE::to_plain(out + 8, ay);
             break;
         }
         default:

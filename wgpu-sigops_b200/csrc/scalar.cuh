@@ -10,6 +10,7 @@
 #pragma once
 #include "field.cuh"
 #include "consts_gen.cuh"
+#include "ptab.h"
 #include "modinv.cuh"
 
 namespace sigops {
@@ -291,6 +292,55 @@ SG_HD int recode_digit(const u32* kp, int i) {
     u32 v = kp[w] >> sh;
     if (sh + W > 32) v |= kp[w + 1] << (32 - sh);
     return (int)(v & ((1u << W) - 1u)) - (1 << (W - 1));
+}
+
+// ---- positional fixed-base tables (ptab.h): signed digits of a 256-bit scalar, lowest window first ----
+// kp (9 limbs) = k + pat
+SG_HD void ptab_recode(u32* kp, const u32* k, const PTab& t) {
+    u64 c = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        c += (u64)(i < 8 ? k[i] : 0u) + t.pat[i];
+        kp[i] = (u32)c;
+        c >>= 32;
+    }
+}
+
+// the signed digit of the lowest window of kp, which is then shifted down by one window (1 <= w <= 31)
+SG_HD int ptab_pop_digit(u32* kp, u32 w) {
+    const int d = (int)(kp[0] & ((1u << w) - 1u)) - (int)(1u << (w - 1));
+#pragma unroll
+    for (int i = 0; i < 8; i++) kp[i] = (kp[i] >> w) | (kp[i + 1] << (32 - w));
+    kp[8] >>= w;
+    return d;
+}
+
+// Ask L2 for every entry the scalar k will select, well before the additions need them (the lane-group kernels: a lone
+// warp cannot hide an HBM miss behind other warps).  No-op in the host simulation.
+SG_HD void ptab_prefetch(const PTab& t, const u32* k, int entry_words);
+
+// word offset of entry |d| of window j (d != 0; d == 0 reads entry 1, which the caller discards)
+SG_HD size_t ptab_offset(const PTab& t, u32 j, int d, int entry_words) {
+    const u32 e = d == 0 ? 0u : (u32)(d < 0 ? -d : d) - 1u;
+    return (((size_t)j << (t.w - 1)) + e) * (size_t)entry_words;
+}
+
+SG_HD void ptab_prefetch(const PTab& t, const u32* k, int entry_words) {
+#if SG_PTX
+    u32 kp[9];
+    ptab_recode(kp, k, t);
+#pragma unroll 1
+    for (u32 j = 0; j < t.pos; j++) {
+        const int d = ptab_pop_digit(kp, t.w);
+        const u32* e = t.base + ptab_offset(t, j, d, entry_words);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(e));
+        if (entry_words > 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(e + entry_words - 1));  // 96-byte entries straddle lines
+    }
+#else
+    (void)t;
+    (void)k;
+    (void)entry_words;
+#endif
 }
 
 }  // namespace sigops

@@ -112,12 +112,12 @@ struct Device {
     size_t h_in_cap = 0;
     uint8_t* h_out = nullptr;
     size_t h_out_cap = 0;
-    const u32 *k1g = nullptr, *r1g = nullptr, *edb = nullptr;
+    PTab k1g{}, r1g{}, edb{};  // positional fixed-base tables (ptab.h), resident for the life of the context
     int grid_k1 = 0, grid_r1 = 0, grid_ed = 0, grid_edm = 0, grid_unit = 0;
     int ggrid_k1 = 0, ggrid_r1 = 0, ggrid_ed = 0;  // resident blocks of the lane-group kernels
     float ms_h2d = 0, ms_kernel = 0, ms_d2h = 0;
     uint64_t last_call = 0;
-    bool smem_tables = true;  // SIGOPS_SMEM_TABLES=0 leaves the fixed-base tables in L2
+    size_t table_bytes = 0;
     // persistent worker: runs this device's shard of a multi-device call (no std::thread spawn / join per call)
     std::thread worker;
     std::mutex wmu;
@@ -277,9 +277,9 @@ void free_device(Device& d) {
     if (d.scratch) cudaFree(d.scratch);
     if (d.h_in) cudaFreeHost(d.h_in);
     if (d.h_out) cudaFreeHost(d.h_out);
-    if (d.k1g) cudaFree((void*)d.k1g);
-    if (d.r1g) cudaFree((void*)d.r1g);
-    if (d.edb) cudaFree((void*)d.edb);
+    if (d.k1g.base) cudaFree((void*)d.k1g.base);
+    if (d.r1g.base) cudaFree((void*)d.r1g.base);
+    if (d.edb.base) cudaFree((void*)d.edb.base);
     for (auto& e : d.ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : d.ev_in)
@@ -316,18 +316,42 @@ int init_device(Device& d, int id, int index, int copy_threads) {
     for (auto& e : d.ev_k) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : d.ev_down) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&d.scratch_ev, cudaEventDisableTiming));
-    // fixed-base tables: computed on the device once, resident for the life of the context (L2-sized: 576 KB)
-    u32 *k1t = nullptr, *r1t = nullptr, *edt = nullptr;
-    CK(cudaMalloc((void**)&k1t, (size_t)2 * kGTabEntries * 16 * sizeof(u32)));
-    d.k1g = k1t;
-    CK(cudaMalloc((void**)&r1t, (size_t)kGTabEntries * 16 * sizeof(u32)));
-    d.r1g = r1t;
-    CK(cudaMalloc((void**)&edt, (size_t)kGTabEntries * 24 * sizeof(u32)));
-    d.edb = edt;
-    CK(kl_gen_tables(d.stream, k1t, r1t, edt));
-    CK(cudaStreamSynchronize(d.stream));
-    g_launches++;
-    if (const char* e = getenv("SIGOPS_SMEM_TABLES")) d.smem_tables = atoi(e) != 0;
+    // positional fixed-base tables (ptab.h): computed on the device once, resident for the life of the context
+    {
+        u32 w = kPTabDefaultWin;
+        if (const char* e = getenv("SIGOPS_GWIN")) {
+            const int v = atoi(e);
+            if (v < (int)kPTabMinWin || v > (int)kPTabMaxWin) {
+                char b[160];
+                snprintf(b, sizeof b, "SIGOPS_GWIN=%s: the fixed-base window must be %u..%u bits", e, kPTabMinWin, kPTabMaxWin);
+                set_err(b);
+                return 1;
+            }
+            w = (u32)v;
+        }
+        const size_t entries = ptab_entries(w);
+        u32* bases = nullptr;
+        CK(cudaMalloc((void**)&bases, (size_t)ptab_positions(w) * 24 * sizeof(u32)));
+        PTab* tabs[3] = {&d.k1g, &d.r1g, &d.edb};
+        for (int c = 0; c < 3; c++) {
+            u32* t = nullptr;
+            const cudaError_t e = cudaMalloc((void**)&t, entries * (c == 2 ? 24 : 16) * sizeof(u32));
+            if (e != cudaSuccess) {
+                cudaFree(bases);
+                char b[200];
+                snprintf(b, sizeof b, "fixed-base table of %zu entries (SIGOPS_GWIN=%u) does not fit on device %d: %s", entries, w, id,
+                         cudaGetErrorString(e));
+                set_err(b);
+                return 1;
+            }
+            ptab_describe(*tabs[c], t, w);
+            CK(kl_gen_ptab(d.stream, c, w, bases, t));
+            CK(cudaStreamSynchronize(d.stream));  // `bases` is reused by the next curve
+            g_launches += 2;
+        }
+        CK(cudaFree(bases));
+        d.table_bytes = entries * (16 + 16 + 24) * sizeof(u32);
+    }
     int per_sm = 0, per_sm2 = 0;
     CK(kl_k1_setup(&per_sm));
     d.grid_k1 = std::max(per_sm, 1) * d.sms;
@@ -526,13 +550,10 @@ int launch_op_scratch(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_
     KLaunch l;
     l.stream = st;
     launch_geometry(d, op, n, &l.grid, &l.tpb);
-    // stage the fixed-base table in shared memory when the launch is big enough to amortise the copy (>= 1 full pass)
-    const bool stage = d.smem_tables && n >= (size_t)d.sms * kBlock;
-    const u32 sw_words = stage ? (u32)kGTabEntries * 16 : 0, ed_words = stage ? (u32)kGTabEntries * 24 : 0;
     switch (op) {
-        case OP_K1: CK(kl_k1_ecrecover(l, d_sigs, d_msgs, n, d_out, d_status, scratch, d.k1g, sw_words)); break;
-        case OP_R1: CK(kl_r1_ecrecover(l, d_sigs, d_msgs, n, d_out, d_status, scratch, d.r1g, sw_words)); break;
-        case OP_ED: CK(kl_ed_verify(l, d_sigs, d_msgs, d_pks, n, d_out, scratch, d.edb, ed_words)); break;
+        case OP_K1: CK(kl_k1_ecrecover(l, d_sigs, d_msgs, n, d_out, d_status, scratch, d.k1g)); break;
+        case OP_R1: CK(kl_r1_ecrecover(l, d_sigs, d_msgs, n, d_out, d_status, scratch, d.r1g)); break;
+        case OP_ED: CK(kl_ed_verify(l, d_sigs, d_msgs, d_pks, n, d_out, scratch, d.edb)); break;
     }
     if (!t_capturing) g_launches++;
     return 0;
@@ -1537,7 +1558,7 @@ int sigops_test_unit(int op, const uint32_t* in, size_t n, uint32_t* out) {
     KLaunch l;
     l.stream = d.stream;
     l.tpb = kBlock;
-    if (op >= SIGOPS_UNIT_K1_GROUP_DOUBLE_MUL) {  // the lane-group twins: 32 items per block, no scratch
+    if (op >= SIGOPS_UNIT_K1_GROUP_DOUBLE_MUL && op <= SIGOPS_UNIT_ED_GROUP_MULPT) {  // the lane-group twins: 32 items per block, no scratch
         l.grid = (int)std::min<size_t>((n + kGroupSigs - 1) / kGroupSigs, (size_t)d.sms * 2);
         CK(kl_unit_group(l, op, (const u32*)d.d_in, n, (u32*)d.d_out, d.k1g, d.r1g));
     } else {
