@@ -47,7 +47,11 @@ extern "C" {
  * device_ids == NULL or n_devices <= 0: use every visible CUDA device (or SIGOPS_GPUS=<count> of them).
  * Calling a compute entry point without sigops_init() initialises lazily with the defaults. */
 /* A second sigops_init with an explicit device list that differs from the pool's fails (nonzero): call
- * sigops_shutdown() first.  sigops_init(NULL, 0) on an initialised pool is a no-op. */
+ * sigops_shutdown() first.  sigops_init(NULL, 0) on an initialised pool is a no-op.
+ * Init generates the fixed-base tables of the three curves on each device (csrc/ptab.h; they replace the 16-entry tables of
+ * src/precompute.rs:14-69 that the reference uploads per call): one table per window of SIGOPS_GWIN bits (environment,
+ * 4..24, default 22: 5.6 GB of HBM and 0.4 s per device; 20 -> 1.5 GB, 0.1 s, 0.6 % slower; 16 -> 0.1 GB, 3 % slower).  A
+ * width out of range, or tables that do not fit, fail the init. */
 int sigops_init(const int* device_ids, int n_devices);
 int sigops_shutdown(void);
 int sigops_num_devices(void);

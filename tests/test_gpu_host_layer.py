@@ -248,3 +248,52 @@ def test_queue_over_all_devices_and_device_resident_producer(sigops):
         with pytest.raises(RuntimeError):
             q.close()
         del view
+
+
+_GWIN_CHILD = r"""
+import os, sys
+ROOT = sys.argv[1]
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")]
+import batches, unit_checks as uc
+from simlib import UnitRunner
+import wgpu_sigops_b200 as w
+lib = w.load()
+w_bits = int(os.environ["SIGOPS_GWIN"])
+uc.check_fixed_base(UnitRunner(lib.sigops_test_unit, lib.sigops_test_unit_shape), w_bits)
+for n, env in ((700, "1"), (40000, "0")):           # lane-group kernels, then one signature per thread
+    os.environ["SIGOPS_LANEGROUP"] = env
+    for cid, mod in ((0, w.secp256k1_ecdsa), (1, w.secp256r1_ecdsa)):
+        s, m, pk, st, _ = batches.ecdsa_batch(cid, n, edge_every=53, seed=70 + cid)
+        out, got = mod.ecrecover_with_status(s, m)
+        assert (out == pk).all() and (got == st).all(), (w_bits, cid, n)
+    s, m, p, v, _ = batches.ed25519_batch(n, edge_every=11, seed=73)
+    assert (w.ed25519_eddsa.ecverify_array(s, m, p) == v).all(), (w_bits, n)
+print("ok", w_bits)
+"""
+
+
+@pytest.mark.parametrize("gwin", ["4", "9", "17"])
+def test_fixed_base_window_widths(gwin):
+    """SIGOPS_GWIN: the positional fixed-base tables at other window widths than the default (the width is a run-time
+    parameter of the kernels and of the table generator): unit ops on width-specific edge scalars and both kernel families
+    end to end, in a child process because the tables are built once per context."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SIGOPS_GWIN=gwin)
+    r = subprocess.run([sys.executable, "-c", _GWIN_CHILD, root], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and ("ok " + gwin) in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_fixed_base_window_out_of_range_is_refused():
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, sys.argv[1]); import wgpu_sigops_b200 as w; lib = w.load(); "
+            "rc = lib.sigops_init(None, 0); print('rc', rc, lib.sigops_last_error().decode())")
+    for bad in ("3", "25", "abc"):
+        r = subprocess.run([sys.executable, "-c", code, root], env=dict(os.environ, SIGOPS_GWIN=bad), capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0 and "rc 0" not in r.stdout and "SIGOPS_GWIN" in r.stdout, r.stdout + r.stderr
