@@ -126,7 +126,7 @@ int hostsim_group_ecrecover(int curve, const uint8_t* sigs, const uint8_t* msgs,
             memcpy(sig_w, sigs + 64 * i, 64);
             memcpy(msg_w, msgs + 32 * i, 32);
             const bool writer = curve == 0 ? sw_ecrecover_group<CurveK1>(sig_w, msg_w, out_w, &st, tab, k1_gtab, g)
-                                           : sw_ecrecover_group<CurveR1>(sig_w, msg_w, out_w, &st, tab, r1_gtab, g);
+                                           : sw_ecrecover_group<ColdProducts<CurveR1> >(sig_w, msg_w, out_w, &st, tab, r1_gtab, g);
             if (writer) {
                 memcpy(out + 64 * i, out_w, 64);
                 if (status) status[i] = (uint8_t)st;
@@ -147,7 +147,7 @@ int hostsim_group_ed25519_verify(const uint8_t* sigs, const uint8_t* msgs, const
             memcpy(sig_w, sigs + 64 * i, 64);
             memcpy(msg_w, msgs + 32 * i, 32);
             memcpy(pk_w, pks + 32 * i, 32);
-            const u32 v = ed_verify_group(sig_w, msg_w, pk_w, tab, ed_btab, g);
+            const u32 v = (i & 1) ? ed_verify_group<true>(sig_w, msg_w, pk_w, tab, ed_btab, g) : ed_verify_group<false>(sig_w, msg_w, pk_w, tab, ed_btab, g);
             if (role == 0) valid[i] = (uint8_t)v;
             g.sync();
         }

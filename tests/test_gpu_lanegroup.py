@@ -19,9 +19,12 @@ import unit_checks as uc
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture
-def forced(monkeypatch):
+@pytest.fixture(params=["products_inlined", "products_out_of_line"])
+def forced(monkeypatch, request):
+    """Every size through the lane-group kernels, once per flavour (the host switches from inlined to out-of-line field
+    products at SIGOPS_GROUP_COLD_MIN signatures; secp256r1 always runs the out-of-line one)."""
     monkeypatch.setenv("SIGOPS_FORCE_LANEGROUP", "1")
+    monkeypatch.setenv("SIGOPS_GROUP_COLD_MIN", "0" if request.param == "products_out_of_line" else "1000000000")
 
 
 def test_group_unit_shims(gpu_units):

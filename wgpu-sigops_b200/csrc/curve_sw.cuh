@@ -139,6 +139,16 @@ struct CurveR1T {
 };
 typedef CurveR1T<FpR1> CurveR1;
 
+// The same curve with the "hot" flavour mapped to the out-of-line products: a kernel instantiated on ColdProducts<C> calls the
+// one copy of each field product instead of inlining it at every site.  The lane-group kernels (group.cuh) use it where the
+// role programs' instruction fetch costs more than the calls: P-256 always (inlined, its request time grows from 0.78 ms at
+// 32 blocks to 1.32 ms at 148; out of line it stays at 0.78-0.79), secp256k1 and ed25519 above ~2,000 signatures
+// (profiles/r02_group_cold_products.txt).
+template <class C>
+struct ColdProducts : C {
+    typedef typename C::Cold Hot;
+};
+
 // P <- 2P.  a = 0: dbl-2009-l (2M + 5S);  a = -3: dbl-2001-b (3M + 5S).  No point of order 2 on either curve.
 template <class C>
 SG_HD void jac_dbl(JacPoint& P) {
@@ -189,6 +199,40 @@ SG_HD void jac_dbl(JacPoint& P) {
         F::template shl<3>(gamma, gamma);  // 8*gamma^2
         F::sub(P.Y, t, gamma);
     }
+}
+
+// P <- 2P on Y^2 = X^3 + a X + b for an arbitrary a given as a field element (dbl-2007-bl, 2M + 8S): the lane-group
+// kernels build the table of multiples of R on a twist whose a depends on the signature (group.cuh).  Not on a hot path.
+template <class C>
+SG_HD void jac_dbl_a(JacPoint& P, const Fe& a) {
+    typedef typename C::F F;
+    if (P.inf) return;
+    Fe XX, YY, YYYY, ZZ, S, M, t;
+    F::sqr(XX, P.X);
+    F::sqr(YY, P.Y);
+    F::sqr(YYYY, YY);
+    F::sqr(ZZ, P.Z);
+    F::add(t, P.X, YY);
+    F::sqr(t, t);
+    F::sub(t, t, XX);
+    F::sub(t, t, YYYY);
+    F::dbl(S, t);  // S = 2((X + YY)^2 - XX - YYYY) = 4 X YY
+    F::add(t, P.Y, P.Z);
+    F::sqr(t, t);
+    F::sub(t, t, YY);
+    F::sub(P.Z, t, ZZ);  // Z3 = 2 Y Z
+    F::sqr(ZZ, ZZ);
+    F::mul(ZZ, a, ZZ);
+    F::dbl(M, XX);
+    F::add(M, M, XX);
+    F::add(M, M, ZZ);  // M = 3 XX + a ZZ^2
+    F::sqr(t, M);
+    F::sub(t, t, S);
+    F::sub(P.X, t, S);  // X3 = M^2 - 2 S
+    F::sub(t, S, P.X);
+    F::mul(t, M, t);
+    F::template shl<3>(YYYY, YYYY);
+    F::sub(P.Y, t, YYYY);  // Y3 = M (S - X3) - 8 YYYY
 }
 
 // shared tail of the two additions: given U1,S1 (of P), H = U2-U1, r = S2-S1 and Zm = Z1*Z2 (or Z1), H != 0
@@ -286,8 +330,9 @@ static constexpr int kSwTabZ = 32, kSwTabC = 46;
 // Step 1 of the table: the Jacobian multiples 2R..8R (X, Y parked in their final slots, Z in the temp area) and the
 // running product of their Z (prefix products stored per entry).  `c` is the running product on entry and exit, so the
 // chain can span several signatures' tables (one shared inversion for all of them).
-template <class C>
-SG_HD void sw_table_park(const TabRef& tab, const Fe& x, const Fe& y, Fe& c) {
+// kTwistA: (x, y) lives on a curve with the coefficient a = a_tw instead of the curve's own (the twist of group.cuh).
+template <class C, bool kTwistA>
+SG_HD void sw_table_park_a(const TabRef& tab, const Fe& x, const Fe& y, Fe& c, const Fe& a_tw) {
     typedef typename C::F F;
     tab_store_fe(tab, 0, x);
     tab_store_fe(tab, 2, y);
@@ -297,12 +342,19 @@ SG_HD void sw_table_park(const TabRef& tab, const Fe& x, const Fe& y, Fe& c) {
         P1.Y = y;
         F::set_one(P1.Z);
         P1.inf = false;
+#define SG_TDBL(P)                \
+    do {                          \
+        if (kTwistA)              \
+            jac_dbl_a<C>(P, a_tw); \
+        else                      \
+            jac_dbl<C>(P);        \
+    } while (0)
         P2 = P1;
-        jac_dbl<C>(P2);
+        SG_TDBL(P2);
         P3 = P2;
         jac_madd<C>(P3, x, y);
         P4 = P2;
-        jac_dbl<C>(P4);
+        SG_TDBL(P4);
 #define SG_PARK(e, P)                           \
     tab_store_fe(tab, 4 * (e), (P).X);          \
     tab_store_fe(tab, 4 * (e) + 2, (P).Y);      \
@@ -314,14 +366,15 @@ SG_HD void sw_table_park(const TabRef& tab, const Fe& x, const Fe& y, Fe& c) {
         jac_madd<C>(T, x, y);
         SG_PARK(4, T);  // 5R
         T = P3;
-        jac_dbl<C>(T);
+        SG_TDBL(T);
         SG_PARK(5, T);  // 6R
         jac_madd<C>(T, x, y);
         SG_PARK(6, T);  // 7R
         T = P4;
-        jac_dbl<C>(T);
+        SG_TDBL(T);
         SG_PARK(7, T);  // 8R
 #undef SG_PARK
+#undef SG_TDBL
     }
     // prefix products (R has prime order n > 8: no multiple is infinity, every Z_j != 0)
     Fe z;
@@ -331,6 +384,11 @@ SG_HD void sw_table_park(const TabRef& tab, const Fe& x, const Fe& y, Fe& c) {
         F::mul(c, c, z);
         tab_store_fe(tab, kSwTabC + 2 * (j - 2), c);
     }
+}
+
+template <class C>
+SG_HD void sw_table_park(const TabRef& tab, const Fe& x, const Fe& y, Fe& c) {
+    sw_table_park_a<C, false>(tab, x, y, c, x);
 }
 
 // Step 2: given inv = (running product after this table)^-1 and c_before = the running product before this table, walk

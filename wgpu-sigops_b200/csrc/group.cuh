@@ -23,6 +23,7 @@
 // per-signature table while role 1 computes r^-1 mod n, u1, u2 and the GLV split / window recoding.
 // Bit-exact with the one-thread-per-signature kernels by construction (same decision procedure, same field arithmetic).
 #pragma once
+#include <type_traits>
 #include "curve_ed.cuh"
 
 namespace sigops {
@@ -83,7 +84,7 @@ struct GroupCtx {
 // ---------------------------------------------------------------------------------------------------------
 template <class C>
 SG_HD void pj_dbl_g(Fe& X, Fe& Y, Fe& Z, const GroupCtx& g) {
-    typedef typename C::Hot HC;
+    typedef typename C::Hot HC;  // ColdProducts<C> (curve_sw.cuh) turns this into the out-of-line flavour
     typedef typename HC::F F;
     Fe t, u, v;
     if (C::kAIsZero) {
@@ -254,7 +255,7 @@ SG_HD void pj_dbl_g(Fe& X, Fe& Y, Fe& Z, const GroupCtx& g) {
 // identity.  `commit` == false (window digit 0): every thread still walks both levels (barriers) and the result is dropped.
 template <class C>
 SG_HD void pj_madd_g(Fe& X, Fe& Y, Fe& Z, const Fe& x2, const Fe& y2, bool commit, const GroupCtx& g) {
-    typedef typename C::Hot HC;
+    typedef typename C::Hot HC;  // ColdProducts<C> (curve_sw.cuh) turns this into the out-of-line flavour
     typedef typename HC::F F;
     Fe t, u, v, w;
     if (C::kAIsZero) {
@@ -603,72 +604,61 @@ SG_HD bool sw_ecrecover_group(const u32* sig_w, const u32* msg_w, u32* out_w, u3
     SwParsed p;
     sw_parse<C>(p, sig_w, msg_w);
     constexpr int kKpWords = GroupKp<C>::kWords;
-    if (C::kAIsZero) {
-        // secp256k1: the table of multiples of R is built WITHOUT y, in the shadow of the square-root chain.  With
-        // w = x^3 + 7 = y^2, the map (X, Y) -> (X / w, y Y / w^2) sends E'' : Y^2 = X^3 + 7 w^3 onto the curve, and
-        // P'' = (w x, w^2) on E'' goes to R = (x, y).  The Jacobian formulas for a = 0 do not involve b, so the multiples
-        // e P'' come out of the ordinary table code; w joins the shared inversion (Montgomery's trick), and when y arrives
-        // the y coordinates are scaled by it.  Role 0: y (254 squarings + 13 products); role 2: the table; role 1: scalars.
-        if (g.role == 0) {
-            u32 bad = p.ok ? 0u : 1u;
-            Fe x, y, t, y2;
-            F::from_plain(x, p.r);
-            C::rhs(t, x);
-            fe_sqrt_candidate((F*)0, y, t);
-            F::sqr(y2, y);
-            if (!F::eq(y2, t)) bad = 1u;  // x = r is not on the curve: invalid (the outputs are zeroed; the table is unused)
-            {
-                u32 yp[8];
-                F::to_plain(yp, y);
-                if ((yp[0] & 1u) != p.parity) F::neg(y, y);
-            }
-            g.put(14, y);
-            g.put_word(kKpWords + 1, bad);
-        } else if (g.role == 2) {
-            Fe x, w, xs, ys, c, inv;
-            F::from_plain(x, p.r);
-            C::rhs(w, x);
-            F::mul(xs, w, x);  // P'' = (w x, w^2)
-            F::sqr(ys, w);
-            c = w;
-            sw_table_park<C>(tab, xs, ys, c);
-            fe_inv((F*)0, inv, c);
-            sw_table_normalize<C>(tab, inv, w);  // leaves inv = w^-1
-            Fe om2;
-            F::sqr(om2, inv);
-#pragma unroll 1
-            for (int e = 0; e < kSwTabEntries; e++) {
-                Fe a;
-                tab_load_fe(a, tab, 4 * e);
-                F::mul(a, a, inv);  // x_e = X''_e / w
-                tab_store_fe(tab, 4 * e, a);
-                C::mul_beta(a, a);
-                tab_store_fe(tab, kSwTabChunks + 4 * e, a);
-                tab_load_fe(a, tab, 4 * e + 2);
-                F::mul(a, a, om2);  // y_e / y = Y''_e / w^2
-                tab_store_fe(tab, 4 * e + 2, a);
-            }
-        }
-    } else if (g.role == 0) {
-        // lift x = r, table {1..8} R (affine), plus beta*x and -y per entry
+    // The table of multiples of R is built WITHOUT y, in the shadow of the square-root chain.  With w = x^3 + a x + b = y^2,
+    // the map (X, Y) -> (X / w, y Y / w^2) sends the twist E'' : Y^2 = X^3 + a w^2 X + b w^3 onto the curve, and P'' = (w x, w^2)
+    // on E'' goes to R = (x, y).  The Jacobian formulas never use b, so the multiples e P'' come out of the ordinary table code
+    // -- with the a = 0 doubling on secp256k1, with a general-a doubling (a'' = -3 w^2) on P-256; w joins the shared inversion
+    // (Montgomery's trick), and when y arrives the y coordinates are scaled by it.
+    // Role 0: y (254 squarings + 13 products); role 2: the table; role 1: scalars.
+    if (g.role == 0) {
         u32 bad = p.ok ? 0u : 1u;
         Fe x, y, t, y2;
         F::from_plain(x, p.r);
         C::rhs(t, x);
         fe_sqrt_candidate((F*)0, y, t);
         F::sqr(y2, y);
-        if (!F::eq(y2, t)) {  // x = r is not on the curve: invalid; continue with R = G
-            bad = 1u;
-            F::from_table(x, C::gen());
-            F::from_table(y, C::gen() + 8);
-        }
+        if (!F::eq(y2, t)) bad = 1u;  // x = r is not on the curve: invalid (the outputs are zeroed; the table is unused)
         {
             u32 yp[8];
             F::to_plain(yp, y);
             if ((yp[0] & 1u) != p.parity) F::neg(y, y);
         }
-        sw_group_table<C>(tab, x, y);
+        g.put(14, y);
         g.put_word(kKpWords + 1, bad);
+    } else if (g.role == 2) {
+        Fe x, w, xs, ys, c, inv;
+        F::from_plain(x, p.r);
+        C::rhs(w, x);
+        F::mul(xs, w, x);  // P'' = (w x, w^2)
+        F::sqr(ys, w);
+        c = w;
+        if (C::kAIsZero) {
+            sw_table_park<C>(tab, xs, ys, c);
+        } else {
+            Fe a_tw;  // a'' = -3 w^2
+            F::dbl(a_tw, ys);
+            F::add(a_tw, a_tw, ys);
+            F::neg(a_tw, a_tw);
+            sw_table_park_a<C, true>(tab, xs, ys, c, a_tw);
+        }
+        fe_inv((F*)0, inv, c);
+        sw_table_normalize<C>(tab, inv, w);  // leaves inv = w^-1
+        Fe om2;
+        F::sqr(om2, inv);
+#pragma unroll 1
+        for (int e = 0; e < kSwTabEntries; e++) {
+            Fe a;
+            tab_load_fe(a, tab, 4 * e);
+            F::mul(a, a, inv);  // x_e = X''_e / w
+            tab_store_fe(tab, 4 * e, a);
+            if (C::kGlv) {
+                C::mul_beta(a, a);
+                tab_store_fe(tab, kSwTabChunks + 4 * e, a);
+            }
+            tab_load_fe(a, tab, 4 * e + 2);
+            F::mul(a, a, om2);  // y_e / y = Y''_e / w^2
+            tab_store_fe(tab, 4 * e + 2, a);
+        }
     }
     if (g.role == 1) {
         // r^-1 mod n, u1 = -z/r, u2 = s/r, GLV split, window recoding
@@ -685,7 +675,7 @@ SG_HD bool sw_ecrecover_group(const u32* sig_w, const u32* msg_w, u32* out_w, u3
         g.put_word(kKpWords, flips);
     }
     g.sync();
-    if (C::kAIsZero) {
+    {
         // y has arrived: entry e gets y_e = y (Y''_e / w^2) and -y_e, the entries spread over the roles
         Fe y;
         g.get(y, 14);
@@ -913,10 +903,12 @@ SG_HD void ed_tab_store_g(const TabRef& tab, int e, const EdPoint& P, const Grou
 
 // One signature, kGroupRolesEd cooperating threads; the verdict is returned by role 0 (the other roles return 0).
 // Role 0 decompresses A while role 1 hashes and reduces mod L; the table, the double-scalar loop and nothing else are shared.
+// kCold: field products out of line (smaller role programs: faster once every SM runs a block, see ColdProducts in curve_sw.cuh).
+template <bool kCold>
 SG_HD u32 ed_verify_group(const u32* sig_w, const u32* msg_w, const u32* pk_w, const TabRef& tab, const PTab& btab, const GroupCtx& g) {
     typedef Sc<ModEdL> S;
 #if !defined(SG_NO_HOT_INLINE)
-    typedef Inl<Fp25519> FH;
+    typedef typename std::conditional<kCold, Fp25519, Inl<Fp25519> >::type FH;
 #else
     typedef Fp25519 FH;
 #endif

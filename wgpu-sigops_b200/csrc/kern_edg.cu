@@ -1,61 +1,12 @@
-// ed25519 ecverify, lane-group kernel (small batches), and the lane-group unit-test shim: kernels + launchers.
+// ed25519 ecverify, lane-group kernel (small batches, field products inlined), and the lane-group unit-test shim: kernels + launchers.
 #include <cuda_runtime.h>
 
-#include "group.cuh"
-#include "launch.h"
+#include "kern_group_ed.cuh"
 #include "../../include/sigops.h"
 
 using namespace sigops;
 
 namespace sigops {
-
-__global__ void __launch_bounds__(kGroupRolesEd * 32) ed25519_verify_group_kernel(const Q4* __restrict__ sigs, const Q4* __restrict__ msgs,
-                                                                                  const Q4* __restrict__ pks, size_t n,
-                                                                                  uint8_t* __restrict__ valid,
-                                                                                  const __grid_constant__ PTab btab) {
-    extern __shared__ __align__(16) u32 sg_group_smem[];
-    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-    Q4* mb = reinterpret_cast<Q4*>(sg_group_smem);
-    u32* sc = sg_group_smem + kMbSlots * 8 * kGroupSigs;
-    Q4* tabq = reinterpret_cast<Q4*>(sc + kScWords * kGroupSigs);
-    GroupCtx g;
-    g.role = role;
-    g.mb = mb + lane;
-    g.sc = sc + lane;
-    TabRef tab;
-    tab.base = tabq + lane;
-    tab.stride = kGroupSigs;
-    for (size_t base = (size_t)blockIdx.x * kGroupSigs; base < n; base += (size_t)gridDim.x * kGroupSigs) {
-        size_t i = base + lane;
-        const bool live = i < n;
-        if (!live) i = n - 1;
-        u32 sig_w[16], msg_w[8], pk_w[8];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            Q4 v = sigs[4 * i + q];
-            sig_w[4 * q + 0] = v.x;
-            sig_w[4 * q + 1] = v.y;
-            sig_w[4 * q + 2] = v.z;
-            sig_w[4 * q + 3] = v.w;
-        }
-#pragma unroll
-        for (int q = 0; q < 2; q++) {
-            Q4 v = msgs[2 * i + q];
-            msg_w[4 * q + 0] = v.x;
-            msg_w[4 * q + 1] = v.y;
-            msg_w[4 * q + 2] = v.z;
-            msg_w[4 * q + 3] = v.w;
-            Q4 p = pks[2 * i + q];
-            pk_w[4 * q + 0] = p.x;
-            pk_w[4 * q + 1] = p.y;
-            pk_w[4 * q + 2] = p.z;
-            pk_w[4 * q + 3] = p.w;
-        }
-        const u32 v = ed_verify_group(sig_w, msg_w, pk_w, tab, btab, g);
-        if (role == 0 && live) valid[i] = (uint8_t)v;
-        __syncthreads();
-    }
-}
 
 // unit shim: one item per lane, the roles of a block cooperate on 32 items (ops SIGOPS_UNIT_*_GROUP_*)
 __global__ void __launch_bounds__(kGroupRolesSw * 32) unit_group_kernel(int op, const u32* __restrict__ in, size_t n, u32* __restrict__ out,
@@ -95,17 +46,12 @@ __global__ void __launch_bounds__(kGroupRolesSw * 32) unit_group_kernel(int op, 
 }
 
 int kl_ed_group(const KLaunch& l, const void* sigs, const void* msgs, const void* pks, size_t n, uint8_t* valid, const PTab& btab) {
-    ed25519_verify_group_kernel<<<l.grid, kGroupRolesEd * 32, kGroupEdSmem, l.stream>>>((const Q4*)sigs, (const Q4*)msgs, (const Q4*)pks, n,
-                                                                                       valid, btab);
-    return (int)cudaGetLastError();
+    return launch_ed_group<false>(l, sigs, msgs, pks, n, valid, btab);
 }
 int kl_ed_group_setup(int* max_blocks_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(ed25519_verify_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGroupEdSmem);
+    cudaError_t e = cudaFuncSetAttribute(unit_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGroupSwSmem);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(unit_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGroupSwSmem);
-    if (e != cudaSuccess) return (int)e;
-    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(max_blocks_per_sm, ed25519_verify_group_kernel, kGroupRolesEd * 32,
-                                                              kGroupEdSmem);
+    return setup_ed_group<false>(max_blocks_per_sm);
 }
 int kl_unit_group(const KLaunch& l, int op, const u32* in, size_t n, u32* out, const PTab& k1g, const PTab& r1g) {
     const int roles = op == SIGOPS_UNIT_ED_GROUP_MULPT ? kGroupRolesEd : kGroupRolesSw;

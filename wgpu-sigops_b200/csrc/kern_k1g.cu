@@ -1,4 +1,4 @@
-// secp256k1 ecrecover, lane-group kernel (small batches): instantiation + launcher.
+// secp256k1 ecrecover, lane-group kernel (small batches), field products inlined: instantiation + launcher.
 #include "kern_group_sw.cuh"
 
 namespace sigops {

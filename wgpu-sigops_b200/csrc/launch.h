@@ -37,6 +37,11 @@ int kl_unit_setup(int* max_blocks_per_sm);
 int kl_k1_group(const KLaunch& l, const void* sigs, const void* msgs, size_t n, void* out, uint8_t* status, const PTab& gtab);
 int kl_r1_group(const KLaunch& l, const void* sigs, const void* msgs, size_t n, void* out, uint8_t* status, const PTab& gtab);
 int kl_ed_group(const KLaunch& l, const void* sigs, const void* msgs, const void* pks, size_t n, uint8_t* valid, const PTab& btab);
+// the same kernels with the field products out of line (ColdProducts, curve_sw.cuh); secp256r1 always runs that flavour
+int kl_k1_group_cold(const KLaunch& l, const void* sigs, const void* msgs, size_t n, void* out, uint8_t* status, const PTab& gtab);
+int kl_ed_group_cold(const KLaunch& l, const void* sigs, const void* msgs, const void* pks, size_t n, uint8_t* valid, const PTab& btab);
+int kl_k1_group_cold_setup(int* max_blocks_per_sm);
+int kl_ed_group_cold_setup(int* max_blocks_per_sm);
 int kl_k1_group_setup(int* max_blocks_per_sm);
 int kl_r1_group_setup(int* max_blocks_per_sm);
 int kl_ed_group_setup(int* max_blocks_per_sm);

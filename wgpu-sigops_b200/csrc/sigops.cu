@@ -362,6 +362,8 @@ int init_device(Device& d, int id, int index, int copy_threads) {
     d.grid_edm = std::max(per_sm2, 1) * d.sms;
     CK(kl_unit_setup(&per_sm));
     d.grid_unit = std::max(per_sm, 1) * d.sms;
+    CK(kl_k1_group_cold_setup(&per_sm));
+    CK(kl_ed_group_cold_setup(&per_sm));
     CK(kl_k1_group_setup(&per_sm));
     d.ggrid_k1 = std::max(per_sm, 1) * d.sms;
     CK(kl_r1_group_setup(&per_sm));
@@ -505,14 +507,17 @@ size_t tail_split(const Device& d, size_t n) {  // signatures in the main launch
 // Small batches run on the lane-group kernels (group.cuh: several cooperating warps per 32 signatures, no device scratch):
 // below one block per SM the request's latency is one signature's dependent chain, which the group kernels cut roughly in
 // half.  SIGOPS_LANEGROUP=0 disables them, SIGOPS_FORCE_LANEGROUP=1 uses them for every size (tests),
-// SIGOPS_LANEGROUP_MAX=<n> moves the threshold.  Defaults from profiles/r02_latency_sweep.json: secp256k1 and ed25519 win
-// while the request fits ONE 32-signature block per SM (4,736 signatures: 0.48 / 0.54 ms against 0.84 / 0.96) -- with two
-// blocks per SM the roles no longer have a scheduler to themselves and the one-thread-per-signature kernel is as fast
-// (0.85 ms); secp256r1 -- three-level formulas, heavier field -- only up to ~1,400 signatures (0.91 ms against 1.15).
+// SIGOPS_LANEGROUP_MAX=<n> moves the threshold.  Defaults from profiles/r02_latency*.txt: all three curves win while the
+// request fits ONE 32-signature block per SM (4,736 signatures: 0.40 / 0.79 / 0.47 ms against 0.80 / 1.12 / 0.93) -- with two
+// blocks per SM the roles no longer have a scheduler to themselves and the one-thread-per-signature kernel is as fast.
+// Above kGroupColdMin signatures secp256k1 and ed25519 switch to the flavour with out-of-line field products (launch_group):
+// inlined wins up to 3,072 signatures (0.391 / 0.456 ms against 0.396 / 0.461), out of line from 4,096 (0.400 / 0.469 against
+// 0.405 / 0.476; 4,736: 0.404 / 0.471 against 0.421 / 0.497) -- profiles/r02_group_flavours.txt.
+constexpr int kGroupColdMin = 3584;
 bool use_group_kernel(const Device& d, Op op, size_t n) {
     if (env_int("SIGOPS_FORCE_LANEGROUP", 0) != 0) return true;
     if (env_int("SIGOPS_LANEGROUP", 1) == 0) return false;
-    const int dflt = op == OP_R1 ? 1408 : d.sms * kGroupSigs;
+    const int dflt = d.sms * kGroupSigs;
     const int lim = env_int("SIGOPS_LANEGROUP_MAX", dflt);
     return n <= (size_t)std::max(lim, 0);
 }
@@ -524,10 +529,23 @@ int launch_group(Device& d, Op op, const uint8_t* d_sigs, const uint8_t* d_msgs,
     l.tpb = 0;
     const int resident = op == OP_K1 ? d.ggrid_k1 : op == OP_R1 ? d.ggrid_r1 : d.ggrid_ed;
     l.grid = (int)std::min<size_t>((n + kGroupSigs - 1) / kGroupSigs, (size_t)resident);
+    // flavour: field products inlined into the role programs while the request occupies a minority of the SMs, out of line
+    // (smaller programs, less instruction fetch through L2) beyond SIGOPS_GROUP_COLD_MIN signatures; P-256 always out of line
+    const bool cold = n > (size_t)std::max(0, env_int("SIGOPS_GROUP_COLD_MIN", kGroupColdMin));
     switch (op) {
-        case OP_K1: CK(kl_k1_group(l, d_sigs, d_msgs, n, d_out, d_status, d.k1g)); break;
+        case OP_K1:
+            if (cold)
+                CK(kl_k1_group_cold(l, d_sigs, d_msgs, n, d_out, d_status, d.k1g));
+            else
+                CK(kl_k1_group(l, d_sigs, d_msgs, n, d_out, d_status, d.k1g));
+            break;
         case OP_R1: CK(kl_r1_group(l, d_sigs, d_msgs, n, d_out, d_status, d.r1g)); break;
-        case OP_ED: CK(kl_ed_group(l, d_sigs, d_msgs, d_pks, n, d_out, d.edb)); break;
+        case OP_ED:
+            if (cold)
+                CK(kl_ed_group_cold(l, d_sigs, d_msgs, d_pks, n, d_out, d.edb));
+            else
+                CK(kl_ed_group(l, d_sigs, d_msgs, d_pks, n, d_out, d.edb));
+            break;
     }
     if (!t_capturing) g_launches++;
     return 0;
